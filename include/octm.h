@@ -1,0 +1,155 @@
+/*
+ * octm.h -- C ABI of the B200 (sm_100a) OCT segmentation-metric kernels.
+ *
+ * Drop-in boundary for the evaluation-metric suite of
+ * ZhangHH233/Retinal_OCT_Image_Segmentation_via_Deep_Learning (directory Metrics/).  The
+ * reference has no FFI: its boundary is 17 Python functions f(y_true, y_pred) -> scalar.  The
+ * Python modules under retinal_oct_image_segmentation_via_deep_learning_b200/Metrics keep those
+ * names and signatures and call the entry points below through ctypes (see INTEGRATION.md for
+ * the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller; the library never allocates,
+ *     frees or synchronises; scratch comes from a caller workspace sized by a *_workspace_bytes
+ *     query; every launch goes on the caller's cudaStream_t, passed as void*.
+ *   - label maps are uint8 [n_items][H][W], C-contiguous, values < K (2 <= K <= 16); a value >= K
+ *     is undefined behaviour for the fast kernels (checked only by octm_validate_labels_u8).
+ *   - return value: OCTM_OK or a negative OCTM_ERR_*; octm_last_error() gives the thread-local
+ *     message of the last failure.
+ *   - outputs are fully overwritten (no pre-zeroing needed) unless stated otherwise.
+ */
+#ifndef OCTM_H_
+#define OCTM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCTM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OCTM_API __attribute__((visibility("default")))
+#else
+#define OCTM_API
+#endif
+
+#define OCTM_OK 0
+#define OCTM_ERR_INVALID (-1)     /* bad pointer / shape / K */
+#define OCTM_ERR_UNSUPPORTED (-2) /* shape outside what the kernels handle */
+#define OCTM_ERR_LAUNCH (-3)      /* CUDA launch or attribute call failed */
+#define OCTM_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define OCTM_MAX_CLASSES 16
+#define OCTM_NO_SEED 0xFFFFFFFFu
+
+OCTM_API int octm_abi_version(void);
+OCTM_API const char* octm_last_error(void);
+
+/* Number of launches of this library's kernels since load (all entry points, this process). */
+OCTM_API uint64_t octm_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  confusion matrix.  counts[i][t][p] = #{pixels of item i with y_true == t and y_pred == p}.
+ * One K x K uint64 matrix per item replaces the reference's per-class recomputation of
+ *   np.sum(y_true * y_pred), np.sum((1 - y_true) * (1 - y_pred)), ...
+ * (Metrics/ConfusionMatrix_based_metrics.py:14-17, 30-32, 45-47, 60-62;
+ *  Metrics/Region_based_metrics.py:13-15, 28-30, 43-45, 58-60; binary-mask forms of
+ *  Metrics/PixelError_based_metrics.py:14-17, Metrics/Contour_based_metrics.py:68-71 and
+ *  Metrics/Biomarker_based_metrics.py:34-38).  item_elems = H*W; items need not be 2-D here. */
+OCTM_API int octm_confusion_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items,
+                      int64_t item_elems, int num_classes, uint64_t* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  column (A-scan) scan.  For every item and column x:
+ *   thickness_c(x) = #{y : L[y][x] == c}          (np.sum(mask, axis=0),
+ *                                                  Metrics/Biomarker_based_metrics.py:14-15)
+ *   boundary  b_k(x) = #{y : L[y][x] < k}, k=1..K-1 (build-defined)
+ * Outputs (any may be NULL):
+ *   thick_absdiff[i][c]   = sum_x |thickness_c^true(x) - thickness_c^pred(x)|   int64 [n][K]
+ *                           (numerator of thickness_difference, Biomarker_based_metrics.py:18-21)
+ *   bnd_sq[i][k-1]        = sum_x (b_k^true(x) - b_k^pred(x))^2                 int64 [n][K-1]
+ *   bnd_abs[i][k-1]       = sum_x |b_k^true(x) - b_k^pred(x)|                   int64 [n][K-1]
+ *                           (numerators of mean_squared_error / mad on boundary arrays,
+ *                            PixelError_based_metrics.py:14-17, Contour_based_metrics.py:68-71)
+ *   bnd_true / bnd_pred   = b_k(x)                                              int32 [n][K-1][W] */
+OCTM_API int octm_column_scan_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                        int num_classes, int64_t* thick_absdiff, int64_t* bnd_sq, int64_t* bnd_abs,
+                        int32_t* bnd_true, int32_t* bnd_pred, void* stream);
+
+/* K3  boundary-position error on caller-supplied boundary arrays int32 [n][Kb][W]
+ * (e.g. positions produced by a layer model): sum_sq[i][k], sum_abs[i][k] as int64 [n][Kb]. */
+OCTM_API int octm_boundary_error_i32(const int32_t* bnd_true, const int32_t* bnd_pred, int64_t n_items,
+                            int num_boundaries, int W, int64_t* sum_sq, int64_t* sum_abs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused label pass: K1 + K2 + K3 + contour seeds in ONE read of both label tensors.
+ *   counts, thick_absdiff, bnd_sq, bnd_abs, bnd_true, bnd_pred : as above, any may be NULL
+ *   first_pos  uint32 [n][2][K] : raster index (y*W + x) of the first pixel of class c in y_true
+ *                                 ([i][0][c]) and y_pred ([i][1][c]); OCTM_NO_SEED if absent.
+ *                                 This is what locates contour [0] (see octm_contour2d_u8). */
+OCTM_API int octm_label_pass_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                       int num_classes, uint64_t* counts, int64_t* thick_absdiff, int64_t* bnd_sq,
+                       int64_t* bnd_abs, int32_t* bnd_true, int32_t* bnd_pred, uint32_t* first_pos,
+                       void* stream);
+
+/* Which implementation octm_label_pass_u8 / K1 / K2 would use for this shape:
+ * 1 = TMA-staged column-strip kernel, 0 = generic kernel. */
+OCTM_API int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred);
+
+/* max label over the whole tensor -> *max_label (device uint32); for input validation. */
+OCTM_API int octm_validate_labels_u8(const uint8_t* labels, int64_t n_elems, uint32_t* max_label, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Contour metrics (2-D): hausdorff_distance, hausdorff_distance_95, assd of
+ * Metrics/Contour_based_metrics.py:5-56, per item and class, on masks (L == c).
+ * Semantics reproduced literally: only contour [0] of skimage.measure.find_contours(mask, 0.5)
+ * (the iso-contour through the raster-first mixed 2x2 square; a closed contour repeats one
+ * vertex).  Vertices live on the doubled lattice (2H-1) x (2W-1); all distances are exact integer
+ * squared lattice distances D2, so a reference distance is sqrt(D2 / 4.0) bit-exactly.
+ *
+ * Per (item i, class c); direction 0 = "for each pred vertex, nearest true vertex" (d1 of the
+ * reference), direction 1 = "for each true vertex, nearest pred vertex" (d2):
+ *   n_pts     uint32 [n][K][2]    vertices of contour [0] of y_true ([0]) / y_pred ([1]) incl. the
+ *                                 closing repeat; 0 = mask has no contour (reference: IndexError)
+ *   flags     uint32 [n][K]       OCTM_CF_* bits
+ *   max_sq    uint32 [n][K][2]    max D2 per direction
+ *   p95_sq    uint32 [n][K][2][2] the two order statistics D2[lo], D2[lo+1] that numpy's linear
+ *                                 95th percentile interpolates, lo = floor(0.95*(m-1)) computed
+ *                                 as numpy does; m = number of query vertices of the direction
+ *   sum_dist  double [n][K][2]    sum over query vertices of sqrt(D2 / 4.0)
+ * max_pts bounds the vertices kept per contour (workspace); longer contours set an overflow flag
+ * and their outputs are invalid -- the host retries those items with a larger bound. */
+#define OCTM_CF_TRUE_CLOSED 1u
+#define OCTM_CF_PRED_CLOSED 2u
+#define OCTM_CF_TRUE_OVERFLOW 4u
+#define OCTM_CF_PRED_OVERFLOW 8u
+
+OCTM_API size_t octm_contour2d_workspace_bytes(int64_t n_items, int H, int W, int num_classes, int max_pts);
+
+OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                      int num_classes, const uint32_t* first_pos /* from the label pass, or NULL */,
+                      int max_pts, uint32_t* n_pts, uint32_t* flags, uint32_t* max_sq,
+                      uint32_t* p95_sq, double* sum_dist, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* The two stages of the above, exposed for tests and for callers that want the vertices.
+ *   verts   uint32 [n][K][2][max_pts]  packed (y2 << 16 | x2) doubled-lattice vertices in trace
+ *                                      order (the closing repeat, if any, is the last entry)
+ *   sq_out  uint32 [n][K][2][max_pts]  optional per-query-vertex D2 (direction d stores the D2 of
+ *                                      the vertices of map 1-d... see DESIGN.md), may be NULL */
+OCTM_API int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t item_elems, int num_classes,
+                      uint32_t* first_pos /* [n][K] */, void* stream);
+OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H,
+                            int W, int num_classes, const uint32_t* first_pos, int max_pts,
+                            uint32_t* verts, uint32_t* n_pts, uint32_t* flags, void* stream);
+OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items,
+                            int num_classes, int max_pts, uint32_t* max_sq, uint32_t* p95_sq,
+                            double* sum_dist, uint32_t* sq_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTM_H_ */

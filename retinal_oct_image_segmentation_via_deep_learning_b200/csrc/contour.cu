@@ -1,0 +1,403 @@
+// Contour metrics (hausdorff_distance, hausdorff_distance_95, assd) -- sm_100a.
+//
+// Reference: Metrics/Contour_based_metrics.py:5-56.  Each function takes
+//     A = skimage.measure.find_contours(y_true, 0.5)[0],  B = find_contours(y_pred, 0.5)[0]
+// (lines 15-16, 33-34, 50-51) and brute-forces  d1 = [min_a |a - p| for p in B],
+// d2 = [min_b |b - p| for p in A]  (lines 19-20, 36-37, 53-54).
+//
+// What contour [0] is for a binary mask (restated in
+// oracle/contours_oracle.py): marching squares over 2x2 pixel squares in raster order; vertices are
+// the midpoints of "cracks" between unequal 4-neighbours; each square joins its cracks pairwise
+// (saddles keep the two high pixels apart); [0] is the polyline through the FIRST emitted segment.
+// If it closes on itself one vertex is repeated: the `to` end of its raster-last segment.
+//
+//   K5  trace_kernel     one thread per (item, class, map): locate the raster-first mixed square
+//                        from the label pass's first-occurrence table, walk the polyline forward
+//                        (and backward if it is open), emit doubled-lattice vertices.
+//   K6  distance_kernel  one CTA per (item, class): both vertex lists in shared memory; exact
+//                        integer squared distances with the expansion |a|^2 - 2 a.q + |q|^2 so the
+//                        inner loop is 2 IMAD + 1 IMNMX per pair, 4 queries per thread.
+//   K7  (same CTA)       max, sum of sqrt(D2/4) in float64, and a radix select of the two order
+//                        statistics numpy's linear 95th percentile interpolates between.
+#include "common.cuh"
+#include "trace_core.h"
+
+namespace octm {
+
+struct TraceParams {
+    const uint8_t* yt;
+    const uint8_t* yp;
+    long long n_items;
+    int H, W, K, max_pts;
+    const uint32_t* first_pos;   // [n][2][K]
+    uint32_t* verts;             // [n][K][2][max_pts]
+    uint32_t* n_pts;             // [n][K][2]
+    uint32_t* flags;             // [n][K]
+};
+
+__global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int K = prm.K, H = prm.H, W = prm.W;
+    if (gid >= prm.n_items * K * 2) return;
+    // consecutive threads: same item, same map, consecutive classes (they walk nearby pixels)
+    const long long item = gid / (2 * K);
+    const int m = static_cast<int>((gid / K) % 2);
+    const int cls = static_cast<int>(gid % K);
+    const uint8_t* L = (m ? prm.yp : prm.yt) + item * H * static_cast<long long>(W);
+    uint32_t* out = prm.verts + ((item * K + cls) * 2 + m) * static_cast<long long>(prm.max_pts);
+    const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
+    uint32_t npts = 0;
+    bool closed = false, overflow = false;
+
+    // seed: first pixel (raster order) whose mask value differs from pixel (0, 0)
+    uint32_t seed = OCTM_NO_SEED;
+    if (H >= 2 && W >= 2) {
+        const int c00 = L[0];
+        if (cls == c00) {
+            for (int c = 0; c < K; ++c)
+                if (c != c00) seed = min(seed, fp[c]);
+        } else {
+            seed = fp[cls];
+        }
+    }
+    if (seed != OCTM_NO_SEED) {
+        const uint32_t cap = static_cast<uint32_t>(prm.max_pts);
+        const TraceResult r = trace_first_contour(
+            H, W, seed,
+            [&](int rr, int cc) -> int { return __ldg(L + static_cast<long long>(rr) * W + cc) == cls ? 1 : 0; },
+            [&](uint32_t i, uint32_t v) { if (i < cap) out[i] = v; });
+        npts = r.npts;
+        closed = r.closed;
+        overflow = npts > cap;
+    }
+    prm.n_pts[(item * K + cls) * 2 + m] = overflow ? static_cast<uint32_t>(prm.max_pts) : npts;
+    uint32_t f = 0;
+    if (closed) f |= m ? OCTM_CF_PRED_CLOSED : OCTM_CF_TRUE_CLOSED;
+    if (overflow) f |= m ? OCTM_CF_PRED_OVERFLOW : OCTM_CF_TRUE_OVERFLOW;
+    if (f) atomicOr(&prm.flags[item * K + cls], f);
+}
+
+// ------------------------------------------------------------------------------ first occurrence
+// first_pos[i][c] = smallest flat index with label c (OCTM_NO_SEED when absent); CTA per item.
+__global__ void __launch_bounds__(256) first_pos_kernel(const uint8_t* __restrict__ labels, long long n_items,
+                                                        long long item_elems, int K, uint32_t* first_pos, long long out_stride) {
+    __shared__ uint32_t s_first[16];
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (threadIdx.x < 16) s_first[threadIdx.x] = OCTM_NO_SEED;
+        __syncthreads();
+        const uint8_t* L = labels + item * item_elems;
+        // contiguous chunk per thread so its own indices ascend
+        const long long chunk = (item_elems + blockDim.x - 1) / blockDim.x;
+        const long long b = threadIdx.x * chunk, e = min(item_elems, b + chunk);
+        uint32_t seen = 0;
+        for (long long i = b; i < e; ++i) {
+            const uint32_t v = L[i] & 15u;
+            if (!((seen >> v) & 1u)) {
+                seen |= 1u << v;
+                atomicMin(&s_first[v], static_cast<uint32_t>(i));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < K) first_pos[item * out_stride + threadIdx.x] = s_first[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ distances
+struct DistParams {
+    const uint32_t* verts;   // [n][K][2][max_pts]
+    const uint32_t* n_pts;   // [n][K][2]
+    long long n_pairs;       // n * K
+    int max_pts;
+    uint32_t* max_sq;        // [n][K][2]
+    uint32_t* p95_sq;        // [n][K][2][2]
+    double* sum_dist;        // [n][K][2]
+    uint32_t* sq_out;        // [n][K][2][max_pts] or null
+};
+
+constexpr int kDistThreads = 128;
+constexpr int kQ = 4;   // queries per thread per sweep
+
+__device__ __forceinline__ uint32_t block_reduce_max(uint32_t v, uint32_t* scratch) {
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = 0;
+    for (int w = 0; w < kDistThreads / 32; ++w) r = max(r, scratch[w]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ uint32_t block_reduce_min(uint32_t v, uint32_t* scratch) {
+    v = __reduce_min_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = 0xffffffffu;
+    for (int w = 0; w < kDistThreads / 32; ++w) r = min(r, scratch[w]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ uint32_t block_reduce_add(uint32_t v, uint32_t* scratch) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = 0;
+    for (int w = 0; w < kDistThreads / 32; ++w) r += scratch[w];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_reduce_add(double v, double* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0;
+    for (int w = 0; w < kDistThreads / 32; ++w) r += scratch[w];
+    __syncthreads();
+    return r;
+}
+
+// k-th smallest (0-based) of vals[0..m) by 8-bit radix passes; all threads return the value.
+__device__ uint32_t block_select(const uint32_t* vals, int m, uint32_t k, uint32_t vmax, uint32_t* hist /*256*/,
+                                 uint32_t* bcast /*2*/) {
+    uint32_t prefix = 0, maskbits = 0;
+    int shift = vmax >= (1u << 24) ? 24 : (vmax >= (1u << 16) ? 16 : (vmax >= (1u << 8) ? 8 : 0));
+    for (; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += kDistThreads) hist[i] = 0;
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += kDistThreads) {
+            const uint32_t v = vals[j];
+            if ((v & maskbits) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t c[8], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; tot += c[i]; }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const uint32_t excl = incl - tot;
+            if (k >= excl && k < incl) {   // exactly one lane
+                uint32_t run = excl;
+                int d = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (k >= run + c[i]) { run += c[i]; d = i + 1; }
+                    else break;
+                }
+                bcast[0] = static_cast<uint32_t>(lane * 8 + d);
+                bcast[1] = k - run;
+            }
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        maskbits |= 255u << shift;
+        k = bcast[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams prm) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_scr[8];
+    __shared__ double s_dscr[8];
+    __shared__ uint32_t s_bc[2];
+    const int cap = prm.max_pts;
+    int2* pts[2] = {reinterpret_cast<int2*>(dsm), reinterpret_cast<int2*>(dsm) + cap};   // {y<<16|x, y^2+x^2}
+    uint32_t* d2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(cap) * 16);
+
+    for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
+        const uint32_t n0 = prm.n_pts[pair * 2 + 0], n1 = prm.n_pts[pair * 2 + 1];
+        const int n[2] = {static_cast<int>(min(n0, (uint32_t)cap)), static_cast<int>(min(n1, (uint32_t)cap))};
+        if (n[0] == 0 || n[1] == 0) {
+            if (threadIdx.x < 2) {
+                prm.max_sq[pair * 2 + threadIdx.x] = 0;
+                prm.p95_sq[pair * 4 + threadIdx.x * 2] = prm.p95_sq[pair * 4 + threadIdx.x * 2 + 1] = 0;
+                prm.sum_dist[pair * 2 + threadIdx.x] = 0.0;
+            }
+            continue;
+        }
+        __syncthreads();
+        for (int mm = 0; mm < 2; ++mm) {
+            const uint32_t* src = prm.verts + (pair * 2 + mm) * static_cast<long long>(cap);
+            for (int i = threadIdx.x; i < n[mm]; i += kDistThreads) {
+                const uint32_t v = src[i];
+                const int y = v >> 16, x = v & 0xffff;
+                pts[mm][i] = make_int2(static_cast<int>(v), y * y + x * x);
+            }
+        }
+        __syncthreads();
+        // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
+        for (int dir = 0; dir < 2; ++dir) {
+            const int2* qs = pts[1 - dir];
+            const int2* ss = pts[dir];
+            const int nq = n[1 - dir], ns = n[dir];
+            for (int base = 0; base < nq; base += kDistThreads * kQ) {
+                int cy[kQ], cx[kQ], best[kQ], qn[kQ];
+#pragma unroll
+                for (int t = 0; t < kQ; ++t) {
+                    const int j = min(base + t * kDistThreads + static_cast<int>(threadIdx.x), nq - 1);
+                    const int2 q = qs[j];
+                    cy[t] = -2 * static_cast<int>(static_cast<uint32_t>(q.x) >> 16);
+                    cx[t] = -2 * (q.x & 0xffff);
+                    qn[t] = q.y;
+                    best[t] = 0x7fffffff;
+                }
+#pragma unroll 4
+                for (int i = 0; i < ns; ++i) {
+                    const int2 s = ss[i];
+                    const int ay = static_cast<uint32_t>(s.x) >> 16, ax = s.x & 0xffff;
+#pragma unroll
+                    for (int t = 0; t < kQ; ++t) best[t] = min(best[t], ax * cx[t] + (ay * cy[t] + s.y));
+                }
+#pragma unroll
+                for (int t = 0; t < kQ; ++t) {
+                    const int j = base + t * kDistThreads + static_cast<int>(threadIdx.x);
+                    if (j < nq) d2[j] = static_cast<uint32_t>(best[t] + qn[t]);
+                }
+            }
+            __syncthreads();
+            // K7: max, sum of sqrt, two order statistics
+            uint32_t vmax = 0;
+            double dsum = 0.0;
+            for (int j = threadIdx.x; j < nq; j += kDistThreads) {
+                const uint32_t v = d2[j];
+                vmax = max(vmax, v);
+                dsum += sqrt(static_cast<double>(v) / 4.0);
+            }
+            vmax = block_reduce_max(vmax, s_scr);
+            dsum = block_reduce_add(dsum, s_dscr);
+            // numpy linear percentile: virtual index (m - 1) * 0.95, neighbours floor and floor + 1
+            const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);
+            const uint32_t lo = static_cast<uint32_t>(floor(pos));
+            const uint32_t v_lo = block_select(d2, nq, lo, vmax, s_hist, s_bc);
+            uint32_t cnt_le = 0, next_gt = 0xffffffffu;
+            for (int j = threadIdx.x; j < nq; j += kDistThreads) {
+                const uint32_t v = d2[j];
+                cnt_le += v <= v_lo ? 1u : 0u;
+                if (v > v_lo) next_gt = min(next_gt, v);
+            }
+            cnt_le = block_reduce_add(cnt_le, s_scr);
+            next_gt = block_reduce_min(next_gt, s_scr);
+            const uint32_t v_hi = (lo + 1 >= static_cast<uint32_t>(nq) || cnt_le >= lo + 2) ? v_lo : next_gt;
+            if (prm.sq_out != nullptr) {
+                uint32_t* o = prm.sq_out + (pair * 2 + dir) * static_cast<long long>(cap);
+                for (int j = threadIdx.x; j < nq; j += kDistThreads) o[j] = d2[j];
+            }
+            if (threadIdx.x == 0) {
+                prm.max_sq[pair * 2 + dir] = vmax;
+                prm.p95_sq[pair * 4 + dir * 2 + 0] = v_lo;
+                prm.p95_sq[pair * 4 + dir * 2 + 1] = v_hi;
+                prm.sum_dist[pair * 2 + dir] = dsum;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace octm
+
+// ----------------------------------------------------------------------------------- C ABI
+static int check_shape(int64_t n, int H, int W, int K, int max_pts) {
+    if (n < 0) return octm::fail(OCTM_ERR_INVALID, "n_items < 0");
+    if (K < 2 || K > OCTM_MAX_CLASSES) return octm::fail(OCTM_ERR_INVALID, "num_classes %d outside [2, 16]", K);
+    if (H < 1 || W < 1) return octm::fail(OCTM_ERR_INVALID, "H, W must be >= 1");
+    if (H > 8192 || W > 8192)
+        return octm::fail(OCTM_ERR_UNSUPPORTED, "image side > 8192: squared lattice distances leave the int32 kernel range");
+    if (static_cast<long long>(H) * W >= (1ll << 32) - 1) return octm::fail(OCTM_ERR_UNSUPPORTED, "H*W >= 2^32");
+    if (max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "max_pts must be >= 8");
+    return OCTM_OK;
+}
+
+extern "C" int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t item_elems, int num_classes,
+                                 uint32_t* first_pos, void* stream) {
+    if (n_items < 0 || item_elems < 1 || item_elems >= (1ll << 32) - 1 || num_classes < 2 || num_classes > 16)
+        return octm::fail(OCTM_ERR_INVALID, "bad shape");
+    if (n_items == 0) return OCTM_OK;
+    if (!labels || !first_pos) return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    const long long grid = n_items < 148 * 8 ? n_items : 148 * 8;
+    octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        labels, n_items, item_elems, num_classes, first_pos, num_classes);
+    return octm::check_launch("first_pos_kernel");
+}
+
+extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                                       int num_classes, const uint32_t* first_pos, int max_pts, uint32_t* verts,
+                                       uint32_t* n_pts, uint32_t* flags, void* stream) {
+    if (int e = check_shape(n_items, H, W, num_classes, max_pts)) return e;
+    if (n_items == 0) return OCTM_OK;
+    if (!y_true || !y_pred || !first_pos || !verts || !n_pts || !flags) return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n_items * num_classes, s) != cudaSuccess)
+        return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
+    octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags};
+    const long long threads = n_items * num_classes * 2;
+    octm::trace_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(p);
+    return octm::check_launch("trace_kernel");
+}
+
+static size_t dist_smem(int max_pts) { return static_cast<size_t>(max_pts) * 20; }
+
+extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
+                                       int max_pts, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
+                                       uint32_t* sq_out, void* stream) {
+    if (n_items < 0 || num_classes < 1 || max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "bad shape");
+    if (n_items == 0) return OCTM_OK;
+    if (!verts || !n_pts || !max_sq || !p95_sq || !sum_dist) return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    const size_t smem = dist_smem(max_pts);
+    if (smem > static_cast<size_t>(octm::max_optin_smem()) - 4096)
+        return octm::fail(OCTM_ERR_UNSUPPORTED, "max_pts %d needs %zu B of shared memory", max_pts, smem);
+    if (cudaFuncSetAttribute(octm::distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             octm::max_optin_smem() - 4096) != cudaSuccess)
+        return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
+    octm::DistParams p{verts, n_pts, n_items * num_classes, max_pts, max_sq, p95_sq, sum_dist, sq_out};
+    long long grid = n_items * num_classes;
+    const long long cap = static_cast<long long>(octm::sm_count()) * 16;
+    if (grid > cap) grid = cap;
+    octm::distance_kernel<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    return octm::check_launch("distance_kernel");
+}
+
+extern "C" size_t octm_contour2d_workspace_bytes(int64_t n_items, int H, int W, int num_classes, int max_pts) {
+    (void)H; (void)W;
+    if (n_items <= 0 || num_classes < 1 || max_pts < 1) return 0;
+    const size_t verts = static_cast<size_t>(n_items) * num_classes * 2 * max_pts * sizeof(uint32_t);
+    const size_t first = static_cast<size_t>(n_items) * 2 * num_classes * sizeof(uint32_t);
+    return ((verts + 255) & ~static_cast<size_t>(255)) + ((first + 255) & ~static_cast<size_t>(255));
+}
+
+extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                                 int num_classes, const uint32_t* first_pos, int max_pts, uint32_t* n_pts,
+                                 uint32_t* flags, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (int e = check_shape(n_items, H, W, num_classes, max_pts)) return e;
+    if (n_items == 0) return OCTM_OK;
+    if (workspace == nullptr || workspace_bytes < octm_contour2d_workspace_bytes(n_items, H, W, num_classes, max_pts))
+        return octm::fail(OCTM_ERR_WORKSPACE, "workspace too small: need %zu B",
+                          octm_contour2d_workspace_bytes(n_items, H, W, num_classes, max_pts));
+    uint32_t* verts = static_cast<uint32_t*>(workspace);
+    const size_t verts_b = (static_cast<size_t>(n_items) * num_classes * 2 * max_pts * sizeof(uint32_t) + 255) & ~static_cast<size_t>(255);
+    uint32_t* fp_ws = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + verts_b);
+    if (first_pos == nullptr) {
+        // no label pass ran: find the first occurrences of both maps here, interleaved [n][2][K]
+        const long long grid = n_items < 148 * 8 ? n_items : 148 * 8;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(y_true, n_items, static_cast<long long>(H) * W,
+                                                                         num_classes, fp_ws, 2 * num_classes);
+        if (int e = octm::check_launch("first_pos_kernel")) return e;
+        octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(y_pred, n_items, static_cast<long long>(H) * W,
+                                                                         num_classes, fp_ws + num_classes, 2 * num_classes);
+        if (int e = octm::check_launch("first_pos_kernel")) return e;
+        first_pos = fp_ws;
+    }
+    if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, max_pts, verts, n_pts,
+                                        flags, stream))
+        return e;
+    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, max_sq, p95_sq, sum_dist, nullptr, stream);
+}

@@ -1,0 +1,734 @@
+// Fused label pass: confusion matrix (K1) + column scan (K2) + boundary error (K3) + contour
+// seeds, in one read of the two uint8 label tensors.  sm_100a only.
+//
+// Replaces, for all classes at once, the per-class numpy passes of the reference:
+//   Metrics/ConfusionMatrix_based_metrics.py:14-17,30-32,45-47,60-62   (sum-of-products counts)
+//   Metrics/Region_based_metrics.py:13-15,28-30,43-45,58-60
+//   Metrics/Biomarker_based_metrics.py:14-21                            (column sums, |dt|)
+// plus the build-defined boundary positions b_k(x) = #{y : L[y][x] < k}  (SURVEY.md 8a-D).
+//
+// FAST KERNEL (W % 16 == 0, W <= 2048, H <= 4096, K <= 8)
+//   * persistent CTAs, one B-scan at a time; a producer warp streams R-row chunks of both maps
+//     into a shared-memory ring with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) signalling
+//     mbarriers; HBM reads are full contiguous rows regardless of how lanes consume them.
+//   * each consumer warp owns a strip of 128 columns for ALL rows of the item: lane = 8 adjacent
+//     columns (one LDS.64 per map), lanes 0-15 take the even row of a row pair, lanes 16-31 the
+//     odd row.  Column state therefore never crosses warps.
+//   * column scan: labels of 4 pixels are packed into a PRMT selector; one PRMT against an 8-entry
+//     byte LUT yields, for 4 pixels at once, the flags [v >= k1] | [v >= k2] << 4 for a PAIR of
+//     thresholds; flags accumulate in nibble counters (flushed every 14 rows into byte counters,
+//     those every 504 rows into uint16 column totals in shared memory).
+//   * confusion matrix: joint code t*8+p per pixel.  A lane whose 8 pixel pairs share one code
+//     (the common case in segmentation maps) adds 8 to its private uint16 histogram column; the
+//     rare mixed lanes are compacted (ballot + popc) into a per-warp queue and drained 32 entries
+//     at a time, one entry per lane, so the scalar path never runs under divergence.
+//   * per item: column totals -> |thickness diff|, boundary error sums (REDUX warp sums), private
+//     histograms -> K x K counts, one plain store per output element (no global atomics).
+//
+// GENERIC KERNEL: any H, W, K <= 16 (byte loads, shared-memory atomics).  Same outputs.
+#include "common.cuh"
+
+namespace octm {
+
+constexpr int kStrip = 128;        // columns per consumer warp
+constexpr int kQueueCap = 64;      // queue entries (8 pixel pairs each) per warp
+constexpr int kMaxStages = 8;
+constexpr uint32_t kPadWord = 0x08080808u;   // label 8: every PRMT LUT below maps it to 0
+
+struct LabelPassParams {
+    const uint8_t* yt;
+    const uint8_t* yp;
+    long long n_items;
+    int H, W, K;
+    int R;   // rows per stage, multiple of 4
+    int S;   // ring stages
+    unsigned long long* counts;
+    long long* thick;
+    long long* bsq;
+    long long* babs;
+    int* bnd_t;
+    int* bnd_p;
+    unsigned* first_pos;
+};
+
+// shared-memory carve-up of the fast kernel
+constexpr int kOffBars = 0;                    // full[8], empty[8]
+constexpr int kOffCounts = 128;                // u32[256]
+constexpr int kOffSq = kOffCounts + 1024;      // u64[16]
+constexpr int kOffAbs = kOffSq + 128;          // u64[16]
+constexpr int kOffThick = kOffAbs + 128;       // u64[16]
+constexpr int kOffFirst = kOffThick + 128;     // u32[2][16]
+constexpr int kOffWarp = 2048;
+constexpr int kWarpTotals = 2 * 8 * kStrip * 2;    // u16 [map][thr][128]
+constexpr int kWarpHist = 64 * 32 * 2;             // u16 [code][lane]
+constexpr int kWarpQueue = kQueueCap * 8;          // uint2 entries
+constexpr int kWarpBytes = kWarpTotals + kWarpHist + kWarpQueue;
+
+__host__ __device__ constexpr uint32_t lut_word(int k1, int k2, int v0) {
+    uint32_t w = 0;
+    for (int i = 0; i < 4; ++i) {
+        int v = v0 + i;
+        uint32_t b = (v >= k1 ? 1u : 0u) | (v >= k2 ? 0x10u : 0u);
+        w |= b << (8 * i);
+    }
+    return w;
+}
+
+// labels of 4 pixels (bytes, each < 16) -> PRMT selector with pixel i in nibble i
+__device__ __forceinline__ uint32_t pack_sel(uint32_t x) {
+    uint32_t t = x | (x >> 4);
+    return __byte_perm(t, 0, 0x4420);   // byte0 <- t.b0, byte1 <- t.b2
+}
+
+template <int NP>
+struct ColState {
+    uint32_t nibT[2][NP], nibP[2][NP];
+    uint32_t bytT[2][2 * NP], bytP[2][2 * NP];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) nibT[s][q] = nibP[s][q] = 0;
+#pragma unroll
+            for (int j = 0; j < 2 * NP; ++j) bytT[s][j] = bytP[s][j] = 0;
+        }
+    }
+    __device__ __forceinline__ void nib_to_byte() {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                bytT[s][2 * q] += nibT[s][q] & 0x0f0f0f0fu;
+                bytT[s][2 * q + 1] += (nibT[s][q] >> 4) & 0x0f0f0f0fu;
+                bytP[s][2 * q] += nibP[s][q] & 0x0f0f0f0fu;
+                bytP[s][2 * q + 1] += (nibP[s][q] >> 4) & 0x0f0f0f0fu;
+                nibT[s][q] = nibP[s][q] = 0;
+            }
+    }
+};
+
+template <int NP>
+__device__ __forceinline__ void col_accumulate(uint32_t (&nib)[2][NP], uint32_t a0, uint32_t a1, uint32_t b0,
+                                               uint32_t b1, uint32_t& pres, bool seeds) {
+    const uint32_t sa[2] = {pack_sel(a0), pack_sel(a1)};
+    const uint32_t sb[2] = {pack_sel(b0), pack_sel(b1)};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const uint32_t lo = lut_word(2 * q + 1, 2 * q + 2, 0), hi = lut_word(2 * q + 1, 2 * q + 2, 4);
+            nib[s][q] = nib[s][q] + __byte_perm(lo, hi, sa[s]) + __byte_perm(lo, hi, sb[s]);
+        }
+        if (seeds) pres |= __byte_perm(0x08040201u, 0x80402010u, sa[s]) | __byte_perm(0x08040201u, 0x80402010u, sb[s]);
+    }
+}
+
+__device__ __forceinline__ void hist_add(unsigned short* hist_lane, uint32_t code, uint32_t inc) {
+    unsigned short* h = hist_lane + code * 32;
+    *h = static_cast<unsigned short>(*h + inc);
+}
+
+__device__ __forceinline__ void drain_entry(unsigned short* hist_lane, uint2 e) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hist_add(hist_lane, (e.x >> (8 * i)) & 0x3fu, 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hist_add(hist_lane, (e.y >> (8 * i)) & 0x3fu, 1);
+}
+
+// one row (8 pixel pairs per lane) into the confusion machinery
+__device__ __forceinline__ void conf_step(uint2 t, uint2 p, bool valid, unsigned short* hist_lane, uint2* queue,
+                                          uint32_t& qhead, uint32_t& qtail, int lane) {
+    const uint32_t j0 = t.x * 8u + p.x, j1 = t.y * 8u + p.y;
+    const uint32_t b = __byte_perm(j0, 0, 0x0000);
+    const bool uni = ((j0 ^ b) | (j1 ^ b)) == 0;
+    if (valid && uni) hist_add(hist_lane, b & 0x3fu, 8);
+    const uint32_t mixed = __ballot_sync(0xffffffffu, valid && !uni);
+    if (mixed) {
+        if (valid && !uni) {
+            const uint32_t pos = qtail + __popc(mixed & lanemask_lt());
+            queue[pos & (kQueueCap - 1)] = make_uint2(j0, j1);
+        }
+        qtail += __popc(mixed);
+        __syncwarp();
+        if (qtail - qhead >= 32) {
+            drain_entry(hist_lane, queue[(qhead + lane) & (kQueueCap - 1)]);
+            qhead += 32;
+            __syncwarp();
+        }
+    }
+}
+
+template <int NP, bool CONF, bool COLS, bool SEEDS, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_pass_fast(const LabelPassParams prm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NW = (blockDim.x >> 5) - 1;
+    const int H = prm.H, W = prm.W, K = prm.K, R = prm.R, S = prm.S;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    uint64_t* empty = full + kMaxStages;
+    uint32_t* cta_counts = reinterpret_cast<uint32_t*>(smem + kOffCounts);
+    unsigned long long* cta_sq = reinterpret_cast<unsigned long long*>(smem + kOffSq);
+    unsigned long long* cta_abs = reinterpret_cast<unsigned long long*>(smem + kOffAbs);
+    unsigned long long* cta_thick = reinterpret_cast<unsigned long long*>(smem + kOffThick);
+    uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + kOffFirst);
+    uint8_t* ring = smem + ((kOffWarp + NW * kWarpBytes + 127) & ~127);
+    const uint32_t map_bytes = static_cast<uint32_t>(R) * W;
+    const uint32_t stage_bytes = 2 * map_bytes;
+
+    for (int i = tid; i < 256; i += blockDim.x) cta_counts[i] = 0;
+    if (tid < 16) cta_sq[tid] = cta_abs[tid] = cta_thick[tid] = 0;
+    if (tid < 32) cta_first[tid] = OCTM_NO_SEED;
+    for (int i = tid; i < NW * kWarpBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + kOffWarp)[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            uint32_t cnt = 0;
+            for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+                const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
+                const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
+                for (int r0 = 0; r0 < H; r0 += R, ++cnt) {
+                    const int rows = min(R, H - r0);
+                    const uint32_t s = cnt % S, ph = (cnt / S) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const uint32_t bytes = static_cast<uint32_t>(rows) * W;
+                    mbar_arrive_expect_tx(&full[s], 2 * bytes);
+                    uint8_t* dst = ring + static_cast<size_t>(s) * stage_bytes;
+                    bulk_g2s(dst, bt + static_cast<long long>(r0) * W, bytes, &full[s], pol);
+                    bulk_g2s(dst + map_bytes, bp + static_cast<long long>(r0) * W, bytes, &full[s], pol);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    uint8_t* wbase = smem + kOffWarp + warp * kWarpBytes;
+    unsigned short* totals = reinterpret_cast<unsigned short*>(wbase);                       // [2][8][128]
+    unsigned short* hist = reinterpret_cast<unsigned short*>(wbase + kWarpTotals);           // [64][32]
+    unsigned short* hist_lane = hist + lane;
+    uint2* queue = reinterpret_cast<uint2*>(wbase + kWarpTotals + kWarpHist);
+    const int phase = lane >> 4;
+    const int col = warp * kStrip + (lane & 15) * 8;      // first of this lane's 8 columns
+    const bool colv = col < W;
+    const int nthr = K - 1;
+    const int consumers = NW * 32;
+
+    ColState<NP> cs;
+    uint32_t cnt = 0;
+    for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+        if (COLS) cs.clear();
+        uint32_t qhead = 0, qtail = 0;
+        uint32_t found = 0;
+        int nib_fill = 0, byt_fill = 0;
+
+        for (int r0 = 0; r0 < H; r0 += R, ++cnt) {
+            const int rows = min(R, H - r0);
+            const uint32_t s = cnt % S, ph = (cnt / S) & 1;
+            mbar_wait(&full[s], ph);
+            const uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes + col;
+            const uint8_t* sp = st + map_bytes;
+            uint32_t presT = 0, presP = 0;
+            const int npairs = (rows + 3) >> 2;
+#pragma unroll 2
+            for (int pr = 0; pr < npairs; ++pr) {
+                const int ra = 4 * pr + phase, rb = ra + 2;
+                const bool va = colv && ra < rows, vb = colv && rb < rows;
+                uint2 tA = make_uint2(kPadWord, kPadWord), pA = tA, tB = tA, pB = tA;
+                if (va) {
+                    tA = *reinterpret_cast<const uint2*>(st + ra * W);
+                    pA = *reinterpret_cast<const uint2*>(sp + ra * W);
+                }
+                if (vb) {
+                    tB = *reinterpret_cast<const uint2*>(st + rb * W);
+                    pB = *reinterpret_cast<const uint2*>(sp + rb * W);
+                }
+                if (COLS || SEEDS) {
+                    col_accumulate<NP>(cs.nibT, tA.x, tA.y, tB.x, tB.y, presT, SEEDS);
+                    col_accumulate<NP>(cs.nibP, pA.x, pA.y, pB.x, pB.y, presP, SEEDS);
+                    if (COLS && ++nib_fill == 7) {
+                        cs.nib_to_byte();
+                        nib_fill = 0;
+                        if (++byt_fill == 18) {
+                            // byte counters could overflow: spill into the uint16 column totals
+                            byt_fill = 0;
+#pragma unroll
+                            for (int hp = 0; hp < 2; ++hp) {
+                                if (phase == hp && colv) {
+#pragma unroll
+                                    for (int j = 0; j < 2 * NP; ++j) {
+                                        uint4* tt = reinterpret_cast<uint4*>(totals + (0 * 8 + j) * kStrip + (lane & 15) * 8);
+                                        uint4* tp = reinterpret_cast<uint4*>(totals + (1 * 8 + j) * kStrip + (lane & 15) * 8);
+                                        uint4 a = *tt, b = *tp;
+                                        a.x += __byte_perm(cs.bytT[0][j], 0, 0x4140);
+                                        a.y += __byte_perm(cs.bytT[0][j], 0, 0x4342);
+                                        a.z += __byte_perm(cs.bytT[1][j], 0, 0x4140);
+                                        a.w += __byte_perm(cs.bytT[1][j], 0, 0x4342);
+                                        b.x += __byte_perm(cs.bytP[0][j], 0, 0x4140);
+                                        b.y += __byte_perm(cs.bytP[0][j], 0, 0x4342);
+                                        b.z += __byte_perm(cs.bytP[1][j], 0, 0x4140);
+                                        b.w += __byte_perm(cs.bytP[1][j], 0, 0x4342);
+                                        *tt = a;
+                                        *tp = b;
+                                        cs.bytT[0][j] = cs.bytT[1][j] = cs.bytP[0][j] = cs.bytP[1][j] = 0;
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+                if (CONF) {
+                    conf_step(tA, pA, va, hist_lane, queue, qhead, qtail, lane);
+                    conf_step(tB, pB, vb, hist_lane, queue, qhead, qtail, lane);
+                }
+            }
+            if (SEEDS) {
+                // classes seen in this stage, by map: bits 0-7 y_true, 8-15 y_pred
+                uint32_t mt = presT | (presT >> 16);
+                mt = (mt | (mt >> 8)) & 0xffu;
+                uint32_t mp = presP | (presP >> 16);
+                mp = (mp | (mp >> 8)) & 0xffu;
+                uint32_t fresh = __reduce_or_sync(0xffffffffu, (mt | (mp << 8)) & ~found);
+                found |= fresh;
+                while (fresh) {
+                    const int bit = __ffs(fresh) - 1;
+                    fresh &= fresh - 1;
+                    const int m = bit >> 3, c = bit & 7;
+                    const uint8_t* sm = m ? sp : st;
+                    const uint32_t cc = 0x01010101u * c;
+                    for (int pp = 0; pp < (rows + 1) / 2; ++pp) {
+                        const int rr = 2 * pp + phase;
+                        uint32_t cand = OCTM_NO_SEED;
+                        if (colv && rr < rows) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(sm + rr * W);
+                            const uint32_t z0 = ~((w.x ^ cc) + 0x7f7f7f7fu) & 0x80808080u;
+                            const uint32_t z1 = ~((w.y ^ cc) + 0x7f7f7f7fu) & 0x80808080u;
+                            if (z0) cand = (r0 + rr) * W + col + ((__ffs(z0) - 1) >> 3);
+                            else if (z1) cand = (r0 + rr) * W + col + 4 + ((__ffs(z1) - 1) >> 3);
+                        }
+                        const uint32_t best = __reduce_min_sync(0xffffffffu, cand);
+                        if (best != OCTM_NO_SEED) {
+                            if (lane == 0) atomicMin(&cta_first[m * 16 + c], best);
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        // ------------------------------------------------------------------ item epilogue
+        if (COLS) {
+            cs.nib_to_byte();
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+                if (phase == hp && colv) {
+#pragma unroll
+                    for (int j = 0; j < 2 * NP; ++j) {
+                        uint4* tt = reinterpret_cast<uint4*>(totals + (0 * 8 + j) * kStrip + (lane & 15) * 8);
+                        uint4* tp = reinterpret_cast<uint4*>(totals + (1 * 8 + j) * kStrip + (lane & 15) * 8);
+                        uint4 a = *tt, b = *tp;
+                        a.x += __byte_perm(cs.bytT[0][j], 0, 0x4140);
+                        a.y += __byte_perm(cs.bytT[0][j], 0, 0x4342);
+                        a.z += __byte_perm(cs.bytT[1][j], 0, 0x4140);
+                        a.w += __byte_perm(cs.bytT[1][j], 0, 0x4342);
+                        b.x += __byte_perm(cs.bytP[0][j], 0, 0x4140);
+                        b.y += __byte_perm(cs.bytP[0][j], 0, 0x4342);
+                        b.z += __byte_perm(cs.bytP[1][j], 0, 0x4140);
+                        b.w += __byte_perm(cs.bytP[1][j], 0, 0x4342);
+                        *tt = a;
+                        *tp = b;
+                    }
+                }
+                __syncwarp();
+            }
+            // per-column arithmetic: lane owns 4 columns of the strip
+            const int lc = lane * 4;
+            const bool cv = warp * kStrip + lc < W;
+            uint32_t sq[2 * NP], ab[2 * NP], th[2 * NP + 1];
+#pragma unroll
+            for (int j = 0; j < 2 * NP; ++j) sq[j] = ab[j] = 0;
+#pragma unroll
+            for (int j = 0; j < 2 * NP + 1; ++j) th[j] = 0;
+            if (cv) {
+                // stream over thresholds k = j + 1: cur = #{label >= k} per column, prev = #{label >= k - 1}
+                int pvt[4] = {H, H, H, H}, pvp[4] = {H, H, H, H};
+                const long long ob = (item * nthr) * W + warp * kStrip + lc;
+#pragma unroll
+                for (int j = 0; j < 2 * NP; ++j) {
+                    uint2* pt = reinterpret_cast<uint2*>(totals + (0 * 8 + j) * kStrip + lc);
+                    uint2* pp = reinterpret_cast<uint2*>(totals + (1 * 8 + j) * kStrip + lc);
+                    const uint2 a = *pt, b = *pp;
+                    *pt = make_uint2(0, 0);
+                    *pp = make_uint2(0, 0);
+                    const int cut[4] = {int(a.x & 0xffff), int(a.x >> 16), int(a.y & 0xffff), int(a.y >> 16)};
+                    const int cup[4] = {int(b.x & 0xffff), int(b.x >> 16), int(b.y & 0xffff), int(b.y >> 16)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int d = cut[i] - cup[i];
+                        sq[j] += d * d;
+                        ab[j] += abs(d);
+                        th[j] += abs((pvt[i] - cut[i]) - (pvp[i] - cup[i]));
+                        pvt[i] = cut[i];
+                        pvp[i] = cup[i];
+                    }
+                    if (prm.bnd_t != nullptr && j < nthr) {
+                        *reinterpret_cast<int4*>(prm.bnd_t + ob + static_cast<long long>(j) * W) =
+                            make_int4(H - cut[0], H - cut[1], H - cut[2], H - cut[3]);
+                        *reinterpret_cast<int4*>(prm.bnd_p + ob + static_cast<long long>(j) * W) =
+                            make_int4(H - cup[0], H - cup[1], H - cup[2], H - cup[3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) th[2 * NP] += abs(pvt[i] - pvp[i]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NP; ++j) {
+                if (j < nthr) {
+                    const uint32_t s1 = __reduce_add_sync(0xffffffffu, sq[j]);
+                    const uint32_t s2 = __reduce_add_sync(0xffffffffu, ab[j]);
+                    if (lane == 0) {
+                        atomicAdd(&cta_sq[j], static_cast<unsigned long long>(s1));
+                        atomicAdd(&cta_abs[j], static_cast<unsigned long long>(s2));
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2 * NP + 1; ++c) {
+                if (c < K) {
+                    const uint32_t s3 = __reduce_add_sync(0xffffffffu, th[c]);
+                    if (lane == 0) atomicAdd(&cta_thick[c], static_cast<unsigned long long>(s3));
+                }
+            }
+        }
+        if (CONF) {
+            // leftover queue entries, then fold the 32 private histogram columns
+            const uint32_t left = qtail - qhead;
+            __syncwarp();
+            if (static_cast<uint32_t>(lane) < left) drain_entry(hist_lane, queue[(qhead + lane) & (kQueueCap - 1)]);
+            __syncwarp();
+            uint32_t* h32 = reinterpret_cast<uint32_t*>(hist);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int code = lane * 2 + cc;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = (lane + i) & 15;
+                    const uint32_t w = h32[code * 16 + j];
+                    h32[code * 16 + j] = 0;
+                    lo += w & 0xffffu;
+                    hi += w >> 16;
+                }
+                if (lo + hi) atomicAdd(&cta_counts[code], lo + hi);
+            }
+        }
+
+        named_bar_sync(1, consumers);
+        {
+            const int ct_id = warp * 32 + lane;
+            if (prm.counts != nullptr) {
+                for (int i = ct_id; i < K * K; i += consumers) {
+                    const int code = (i / K) * 8 + (i % K);
+                    prm.counts[item * K * K + i] = cta_counts[code];
+                }
+            }
+            if (CONF)
+                for (int i = ct_id; i < 64; i += consumers) cta_counts[i] = 0;
+            if (ct_id < 16) {
+                if (COLS) {
+                    if (ct_id < K && prm.thick != nullptr) prm.thick[item * K + ct_id] = static_cast<long long>(cta_thick[ct_id]);
+                    if (ct_id < nthr && prm.bsq != nullptr) prm.bsq[item * nthr + ct_id] = static_cast<long long>(cta_sq[ct_id]);
+                    if (ct_id < nthr && prm.babs != nullptr) prm.babs[item * nthr + ct_id] = static_cast<long long>(cta_abs[ct_id]);
+                    cta_thick[ct_id] = cta_sq[ct_id] = cta_abs[ct_id] = 0;
+                }
+            }
+            if (SEEDS && ct_id < 32) {
+                const int m = ct_id >> 4, c = ct_id & 15;
+                if (c < K && prm.first_pos != nullptr) prm.first_pos[(item * 2 + m) * K + c] = cta_first[ct_id];
+                cta_first[ct_id] = OCTM_NO_SEED;
+            }
+        }
+        named_bar_sync(1, consumers);
+    }
+}
+
+// ------------------------------------------------------------------------------------ generic
+// Any H, W and K <= 16.  One CTA per item (grid-stride); thread = column (stride blockDim).
+template <int NT>   // number of thresholds tracked in registers (K - 1 <= NT)
+__global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams prm) {
+    __shared__ uint32_t s_counts[8][256];
+    __shared__ unsigned long long s_sq[16], s_abs[16], s_thick[16];
+    __shared__ uint32_t s_first[2][16];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int H = prm.H, W = prm.W, K = prm.K, nthr = K - 1;
+    for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+        for (int i = tid; i < 8 * 256; i += 256) (&s_counts[0][0])[i] = 0;
+        if (tid < 16) s_sq[tid] = s_abs[tid] = s_thick[tid] = 0;
+        if (tid < 32) (&s_first[0][0])[tid] = OCTM_NO_SEED;
+        __syncthreads();
+        const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
+        const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
+        for (int x = tid; x < W; x += 256) {
+            uint32_t seen_t = 0, seen_p = 0;   // raster index grows with y inside one column
+            int ct[NT], cp[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) ct[j] = cp[j] = 0;
+            for (int y = 0; y < H; ++y) {
+                const uint32_t t = bt[static_cast<long long>(y) * W + x], p = bp[static_cast<long long>(y) * W + x];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    ct[j] += (t > static_cast<uint32_t>(j)) ? 1 : 0;
+                    cp[j] += (p > static_cast<uint32_t>(j)) ? 1 : 0;
+                }
+                atomicAdd(&s_counts[warp][(t & 15) * 16 + (p & 15)], 1u);
+                if (!((seen_t >> (t & 31)) & 1)) {
+                    seen_t |= 1u << (t & 31);
+                    atomicMin(&s_first[0][t & 15], static_cast<uint32_t>(y * W + x));
+                }
+                if (!((seen_p >> (p & 31)) & 1)) {
+                    seen_p |= 1u << (p & 31);
+                    atomicMin(&s_first[1][p & 15], static_cast<uint32_t>(y * W + x));
+                }
+            }
+            // column arithmetic: ct[j] = #{label >= j+1}
+            int prev_t = H, prev_p = H;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                if (j < nthr) {
+                    const long long d = ct[j] - cp[j];
+                    atomicAdd(&s_sq[j], static_cast<unsigned long long>(d * d));
+                    atomicAdd(&s_abs[j], static_cast<unsigned long long>(d < 0 ? -d : d));
+                    const int dt = (prev_t - ct[j]) - (prev_p - cp[j]);
+                    atomicAdd(&s_thick[j], static_cast<unsigned long long>(dt < 0 ? -dt : dt));
+                    prev_t = ct[j];
+                    prev_p = cp[j];
+                    if (prm.bnd_t != nullptr) {
+                        prm.bnd_t[(item * nthr + j) * W + x] = H - ct[j];
+                        prm.bnd_p[(item * nthr + j) * W + x] = H - cp[j];
+                    }
+                }
+            }
+            {
+                const int dt = prev_t - prev_p;   // last class: count of (label >= K-1)
+                atomicAdd(&s_thick[nthr], static_cast<unsigned long long>(dt < 0 ? -dt : dt));
+            }
+        }
+        __syncthreads();
+        if (prm.counts != nullptr) {
+            for (int i = tid; i < K * K; i += 256) {
+                const int code = (i / K) * 16 + (i % K);
+                unsigned long long sum = 0;
+                for (int w = 0; w < 8; ++w) sum += s_counts[w][code];
+                prm.counts[item * K * K + i] = sum;
+            }
+        }
+        if (tid < K && prm.thick != nullptr) prm.thick[item * K + tid] = static_cast<long long>(s_thick[tid]);
+        if (tid < nthr && prm.bsq != nullptr) prm.bsq[item * nthr + tid] = static_cast<long long>(s_sq[tid]);
+        if (tid < nthr && prm.babs != nullptr) prm.babs[item * nthr + tid] = static_cast<long long>(s_abs[tid]);
+        if (tid < 32 && prm.first_pos != nullptr) {
+            const int m = tid >> 4, c = tid & 15;
+            if (c < K) prm.first_pos[(item * 2 + m) * K + c] = s_first[m][c];
+        }
+        __syncthreads();
+    }
+}
+
+// K3: sums over columns of (bt - bp)^2 and |bt - bp| for int32 boundary arrays [n][Kb][W].
+__global__ void __launch_bounds__(256) boundary_error_kernel(const int* __restrict__ bt, const int* __restrict__ bp,
+                                                             long long n_rows, int W, long long* sum_sq,
+                                                             long long* sum_abs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+    if (row >= n_rows) return;
+    const int* a = bt + row * W;
+    const int* b = bp + row * W;
+    long long sq = 0, ab = 0;
+    for (int x = lane; x < W; x += 32) {
+        const long long d = static_cast<long long>(a[x]) - b[x];
+        sq += d * d;
+        ab += d < 0 ? -d : d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    }
+    if (lane == 0) {
+        sum_sq[row] = sq;
+        sum_abs[row] = ab;
+    }
+}
+
+__global__ void __launch_bounds__(256) max_label_kernel(const uint8_t* __restrict__ x, long long n, uint32_t* out) {
+    uint32_t m = 0;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, (uint32_t)x[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ------------------------------------------------------------------------------------ dispatch
+static bool fast_ok(int H, int W, int K, const void* a, const void* b) {
+    return K >= 2 && K <= 8 && W % 16 == 0 && W >= 16 && W <= 2048 && H >= 1 && H <= 4096 &&
+           (reinterpret_cast<uintptr_t>(a) % 16 == 0) && (reinterpret_cast<uintptr_t>(b) % 16 == 0);
+}
+
+template <int NP, bool CONF, bool COLS, bool SEEDS>
+static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
+    LabelPassParams p = p0;
+    const int NW = (p.W + kStrip - 1) / kStrip;
+    // rows per stage: ~4 KB per map, multiple of 4; 4 stages in flight per CTA
+    int R = (4096 / p.W) & ~3;
+    if (R < 4) R = 4;
+    p.R = R;
+    const int fixed = ((kOffWarp + NW * kWarpBytes + 127) & ~127);
+    const int stage = 2 * R * p.W;
+    const int budget = max_optin_smem();
+    int S = 4;
+    while (S > 2 && fixed + S * stage > budget) --S;
+    p.S = S;
+    const int smem = fixed + S * stage;
+    if (smem > budget) return fail(OCTM_ERR_UNSUPPORTED, "label pass: %d B of shared memory needed", smem);
+    auto kern = NW > 8 ? label_pass_fast<NP, CONF, COLS, SEEDS, true> : label_pass_fast<NP, CONF, COLS, SEEDS, false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess)
+        return fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(label_pass_fast) failed");
+    int per_sm = budget / smem;
+    const int threads = (NW + 1) * 32;
+    if (per_sm * threads > 2048) per_sm = 2048 / threads;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = static_cast<long long>(sm_count()) * per_sm;
+    if (grid > p.n_items) grid = p.n_items;
+    kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p);
+    return check_launch("label_pass_fast");
+}
+
+template <bool CONF, bool COLS, bool SEEDS>
+static int dispatch_np(const LabelPassParams& p, cudaStream_t stream) {
+    const int np = p.K / 2;   // ceil((K-1)/2)
+    switch (np) {
+        case 1: return launch_fast<1, CONF, COLS, SEEDS>(p, stream);
+        case 2: return launch_fast<2, CONF, COLS, SEEDS>(p, stream);
+        case 3: return launch_fast<3, CONF, COLS, SEEDS>(p, stream);
+        default: return launch_fast<4, CONF, COLS, SEEDS>(p, stream);
+    }
+}
+
+static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
+    long long grid = p.n_items < 148 * 8 ? p.n_items : 148 * 8;
+    if (p.K <= 8)
+        label_pass_generic<7><<<static_cast<unsigned>(grid), 256, 0, stream>>>(p);
+    else
+        label_pass_generic<15><<<static_cast<unsigned>(grid), 256, 0, stream>>>(p);
+    return check_launch("label_pass_generic");
+}
+
+int run_label_pass(const LabelPassParams& p, bool conf, bool cols, bool seeds, cudaStream_t stream) {
+    if (p.n_items == 0) return OCTM_OK;
+    if (fast_ok(p.H, p.W, p.K, p.yt, p.yp) && (p.bnd_t == nullptr || reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0) &&
+        (p.bnd_p == nullptr || reinterpret_cast<uintptr_t>(p.bnd_p) % 16 == 0)) {
+        if (conf && cols && seeds) return dispatch_np<true, true, true>(p, stream);
+        if (conf && cols) return dispatch_np<true, true, false>(p, stream);
+        if (conf && !cols && !seeds) return dispatch_np<true, false, false>(p, stream);
+        if (!conf && cols && !seeds) return dispatch_np<false, true, false>(p, stream);
+        return dispatch_np<true, true, true>(p, stream);
+    }
+    return launch_generic(p, stream);
+}
+
+}  // namespace octm
+
+using octm::LabelPassParams;
+
+static int check_common(const void* yt, const void* yp, int64_t n, int K) {
+    if (n < 0) return octm::fail(OCTM_ERR_INVALID, "n_items < 0");
+    if (K < 2 || K > OCTM_MAX_CLASSES) return octm::fail(OCTM_ERR_INVALID, "num_classes %d outside [2, 16]", K);
+    if (n > 0 && (yt == nullptr || yp == nullptr)) return octm::fail(OCTM_ERR_INVALID, "null label pointer");
+    return OCTM_OK;
+}
+
+extern "C" int octm_label_pass_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                                  int num_classes, uint64_t* counts, int64_t* thick_absdiff, int64_t* bnd_sq,
+                                  int64_t* bnd_abs, int32_t* bnd_true, int32_t* bnd_pred, uint32_t* first_pos,
+                                  void* stream) {
+    if (int e = check_common(y_true, y_pred, n_items, num_classes)) return e;
+    if (H < 1 || W < 1) return octm::fail(OCTM_ERR_INVALID, "H, W must be >= 1");
+    if (static_cast<long long>(H) * W >= (1ll << 32)) return octm::fail(OCTM_ERR_UNSUPPORTED, "H*W >= 2^32");
+    if ((bnd_true == nullptr) != (bnd_pred == nullptr)) return octm::fail(OCTM_ERR_INVALID, "bnd_true/bnd_pred: both or neither");
+    LabelPassParams p{};
+    p.yt = y_true; p.yp = y_pred; p.n_items = n_items; p.H = H; p.W = W; p.K = num_classes;
+    p.counts = reinterpret_cast<unsigned long long*>(counts);
+    p.thick = reinterpret_cast<long long*>(thick_absdiff);
+    p.bsq = reinterpret_cast<long long*>(bnd_sq);
+    p.babs = reinterpret_cast<long long*>(bnd_abs);
+    p.bnd_t = bnd_true; p.bnd_p = bnd_pred; p.first_pos = first_pos;
+    const bool conf = counts != nullptr;
+    const bool cols = thick_absdiff || bnd_sq || bnd_abs || bnd_true;
+    const bool seeds = first_pos != nullptr;
+    return octm::run_label_pass(p, conf, cols, seeds, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred) {
+    return octm::fast_ok(H, W, num_classes, y_true, y_pred) ? 1 : 0;
+}
+
+extern "C" int octm_confusion_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int64_t item_elems,
+                                 int num_classes, uint64_t* counts, void* stream) {
+    if (int e = check_common(y_true, y_pred, n_items, num_classes)) return e;
+    if (counts == nullptr) return octm::fail(OCTM_ERR_INVALID, "counts is null");
+    if (item_elems < 1 || item_elems >= (1ll << 32)) return octm::fail(OCTM_ERR_INVALID, "item_elems outside [1, 2^32)");
+    // any factorisation H*W = item_elems gives the same histogram: prefer one the fast kernel takes
+    int H = 1, W = 0;
+    for (int w = 2048; w >= 16; w >>= 1) {
+        if (item_elems % w == 0 && item_elems / w <= 4096) { W = w; H = static_cast<int>(item_elems / w); break; }
+    }
+    if (W == 0) {
+        if (item_elems > 0x7fffffff) return octm::fail(OCTM_ERR_UNSUPPORTED, "item too large for the generic kernel");
+        W = static_cast<int>(item_elems); H = 1;
+        // generic kernel walks columns: make rows long-ish
+        for (int h = 64; h >= 2; --h) if (item_elems % h == 0) { H = h; W = static_cast<int>(item_elems / h); break; }
+    }
+    LabelPassParams p{};
+    p.yt = y_true; p.yp = y_pred; p.n_items = n_items; p.H = H; p.W = W; p.K = num_classes;
+    p.counts = reinterpret_cast<unsigned long long*>(counts);
+    return octm::run_label_pass(p, true, false, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int octm_column_scan_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                                   int num_classes, int64_t* thick_absdiff, int64_t* bnd_sq, int64_t* bnd_abs,
+                                   int32_t* bnd_true, int32_t* bnd_pred, void* stream) {
+    return octm_label_pass_u8(y_true, y_pred, n_items, H, W, num_classes, nullptr, thick_absdiff, bnd_sq, bnd_abs,
+                              bnd_true, bnd_pred, nullptr, stream);
+}
+
+extern "C" int octm_boundary_error_i32(const int32_t* bnd_true, const int32_t* bnd_pred, int64_t n_items,
+                                       int num_boundaries, int W, int64_t* sum_sq, int64_t* sum_abs, void* stream) {
+    if (n_items < 0 || num_boundaries < 1 || W < 1) return octm::fail(OCTM_ERR_INVALID, "bad shape");
+    if (n_items == 0) return OCTM_OK;
+    if (!bnd_true || !bnd_pred || !sum_sq || !sum_abs) return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    const long long rows = n_items * num_boundaries;
+    octm::boundary_error_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bnd_true, bnd_pred, rows, W, reinterpret_cast<long long*>(sum_sq), reinterpret_cast<long long*>(sum_abs));
+    return octm::check_launch("boundary_error_kernel");
+}
+
+extern "C" int octm_validate_labels_u8(const uint8_t* labels, int64_t n_elems, uint32_t* max_label, void* stream) {
+    if (n_elems < 0 || max_label == nullptr || (n_elems > 0 && labels == nullptr)) return octm::fail(OCTM_ERR_INVALID, "bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(max_label, 0, sizeof(uint32_t), s) != cudaSuccess) return octm::fail(OCTM_ERR_LAUNCH, "memset failed");
+    if (n_elems == 0) return OCTM_OK;
+    octm::max_label_kernel<<<148 * 8, 256, 0, s>>>(labels, n_elems, max_label);
+    return octm::check_launch("max_label_kernel");
+}

@@ -1,0 +1,269 @@
+"""Batched, device-resident entry points of the metric suite (the host side of the C ABI).
+
+``y_true`` / ``y_pred`` are CUDA ``torch.uint8`` label maps ``[N, H, W]`` with values ``< num_classes``.
+torch is used only for device memory and streams; all arithmetic on label data happens in the
+hand-written kernels of ``liboctm.so`` (no CPU or torch fallback), and the float64 ratios are
+evaluated on the host from the kernels' exact integers (``derive.py``).
+
+    res = evaluate(y_true, y_pred, num_classes=8)        # one fused label pass + contour kernels
+    res.metrics()["dice_coefficient"]                      # float64 [N, K], reference operation order
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, derive
+
+DEFAULT_MAX_PTS = 2048       # contour vertices kept per (item, class, map) on the first attempt
+MAX_MAX_PTS = 11000          # shared-memory bound of the distance kernel (20 B per vertex)
+CONTOUR_CHUNK_BYTES = 1 << 30
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_pair(y_true, y_pred):
+    for name, t in (("y_true", y_true), ("y_pred", y_pred)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise TypeError(f"{name} must be a CUDA torch tensor (got {type(t).__name__}); "
+                            "use the Metrics/ drop-in functions for host arrays")
+        if t.dtype not in (torch.uint8, torch.bool):
+            raise TypeError(f"{name} must be uint8 (or bool), got {t.dtype}")
+    if y_true.shape != y_pred.shape:
+        raise ValueError(f"shape mismatch: {tuple(y_true.shape)} vs {tuple(y_pred.shape)}")
+    if y_true.device != y_pred.device:
+        raise ValueError("y_true and y_pred are on different devices")
+    if y_true.dim() == 2:
+        y_true, y_pred = y_true[None], y_pred[None]
+    if y_true.dim() != 3:
+        raise ValueError("expected [N, H, W] or [H, W] label maps")
+    cast = lambda t: (t.view(torch.uint8) if t.dtype == torch.bool else t).contiguous()   # noqa: E731
+    return cast(y_true), cast(y_pred)
+
+
+@dataclass
+class LabelPassOut:
+    """Exact integers of the fused label pass (device tensors; u64/u32 stored as int64/int32 bits)."""
+    num_classes: int
+    height: int
+    width: int
+    counts: torch.Tensor | None = None          # [N, K, K]   cm[t][p]
+    thick_absdiff: torch.Tensor | None = None   # [N, K]
+    bnd_sq: torch.Tensor | None = None          # [N, K-1]
+    bnd_abs: torch.Tensor | None = None         # [N, K-1]
+    bnd_true: torch.Tensor | None = None        # [N, K-1, W] int32
+    bnd_pred: torch.Tensor | None = None
+    first_pos: torch.Tensor | None = None       # [N, 2, K]  uint32 bits
+
+
+def label_pass(y_true, y_pred, num_classes, *, counts=True, columns=True, seeds=False, boundaries=False):
+    """One read of both label tensors -> confusion matrices, column-scan sums, contour seeds."""
+    yt, yp = _check_pair(y_true, y_pred)
+    n, h, w = yt.shape
+    k = int(num_classes)
+    dev = yt.device
+    out = LabelPassOut(k, h, w)
+    with torch.cuda.device(dev):
+        if counts:
+            out.counts = torch.empty((n, k, k), dtype=torch.int64, device=dev)
+        if columns or boundaries:
+            out.thick_absdiff = torch.empty((n, k), dtype=torch.int64, device=dev)
+            out.bnd_sq = torch.empty((n, k - 1), dtype=torch.int64, device=dev)
+            out.bnd_abs = torch.empty((n, k - 1), dtype=torch.int64, device=dev)
+        if boundaries:
+            out.bnd_true = torch.empty((n, k - 1, w), dtype=torch.int32, device=dev)
+            out.bnd_pred = torch.empty((n, k - 1, w), dtype=torch.int32, device=dev)
+        if seeds:
+            out.first_pos = torch.empty((n, 2, k), dtype=torch.int32, device=dev)
+        _lib.call("octm_label_pass_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(out.counts), _ptr(out.thick_absdiff),
+                  _ptr(out.bnd_sq), _ptr(out.bnd_abs), _ptr(out.bnd_true), _ptr(out.bnd_pred), _ptr(out.first_pos),
+                  _stream())
+    return out
+
+
+def confusion(y_true, y_pred, num_classes):
+    """K1 alone: ``int64 [N, K, K]`` confusion matrices (items may have any trailing shape)."""
+    for t in (y_true, y_pred):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype not in (torch.uint8, torch.bool):
+            raise TypeError("confusion() takes CUDA uint8/bool tensors")
+    if y_true.shape != y_pred.shape:
+        raise ValueError("shape mismatch")
+    yt = (y_true.view(torch.uint8) if y_true.dtype == torch.bool else y_true).contiguous()
+    yp = (y_pred.view(torch.uint8) if y_pred.dtype == torch.bool else y_pred).contiguous()
+    n = yt.shape[0]
+    elems = yt[0].numel() if n else 1
+    k = int(num_classes)
+    out = torch.empty((n, k, k), dtype=torch.int64, device=yt.device)
+    with torch.cuda.device(yt.device):
+        _lib.call("octm_confusion_u8", _ptr(yt), _ptr(yp), n, elems, k, _ptr(out), _stream())
+    return out
+
+
+def boundary_error(bnd_true, bnd_pred):
+    """K3 alone on caller-supplied ``int32 [N, Kb, W]`` boundary positions -> (sum_sq, sum_abs) int64 [N, Kb]."""
+    if bnd_true.shape != bnd_pred.shape or bnd_true.dim() != 3:
+        raise ValueError("expected two [N, Kb, W] tensors of equal shape")
+    bt, bp = bnd_true.to(torch.int32).contiguous(), bnd_pred.to(torch.int32).contiguous()
+    n, kb, w = bt.shape
+    sq = torch.empty((n, kb), dtype=torch.int64, device=bt.device)
+    ab = torch.empty((n, kb), dtype=torch.int64, device=bt.device)
+    with torch.cuda.device(bt.device):
+        _lib.call("octm_boundary_error_i32", _ptr(bt), _ptr(bp), n, kb, w, _ptr(sq), _ptr(ab), _stream())
+    return sq, ab
+
+
+@dataclass
+class ContourOut:
+    """Exact integers (and the float64 distance sums) of the contour kernels, device tensors."""
+    n_pts: torch.Tensor        # [N, K, 2]   uint32 bits
+    flags: torch.Tensor        # [N, K]
+    max_sq: torch.Tensor       # [N, K, 2]
+    p95_sq: torch.Tensor       # [N, K, 2, 2]
+    sum_dist: torch.Tensor     # [N, K, 2]   float64
+    verts: torch.Tensor | None = None     # [N, K, 2, max_pts] when requested
+    sq: torch.Tensor | None = None        # [N, K, 2, max_pts] when requested
+    max_pts: int = 0
+
+
+def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq):
+    n, h, w = yt.shape
+    dev = yt.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    verts = torch.empty((n, k, 2, max_pts), **i32)
+    n_pts = torch.empty((n, k, 2), **i32)
+    flags = torch.empty((n, k), **i32)
+    max_sq = torch.empty((n, k, 2), **i32)
+    p95 = torch.empty((n, k, 2, 2), **i32)
+    sums = torch.empty((n, k, 2), dtype=torch.float64, device=dev)
+    sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else None
+    _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), max_pts, _ptr(verts),
+              _ptr(n_pts), _ptr(flags), _stream())
+    _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, _ptr(max_sq), _ptr(p95),
+              _ptr(sums), _ptr(sq), _stream())
+    return ContourOut(n_pts, flags, max_sq, p95, sums, verts if want_verts else None, sq, max_pts)
+
+
+def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
+                 return_sq=False):
+    """Contour ``[0]`` of every class mask of both maps, then hausdorff / hd95 / assd integers.
+
+    Items are processed in chunks so the vertex workspace stays under ~1 GiB; items whose contour is
+    longer than ``max_pts`` are re-run on their own with a larger bound."""
+    yt, yp = _check_pair(y_true, y_pred)
+    n, h, w = yt.shape
+    k = int(num_classes)
+    if h < 2 or w < 2:
+        raise ValueError("Input array must be at least 2x2.")     # skimage's message for find_contours
+    dev = yt.device
+    with torch.cuda.device(dev):
+        if first_pos is None:
+            first_pos = torch.empty((n, 2, k), dtype=torch.int32, device=dev)
+            tmp = torch.empty((n, k), dtype=torch.int32, device=dev)
+            for m, src in enumerate((yt, yp)):
+                _lib.call("octm_first_pos_u8", _ptr(src), n, h * w, k, _ptr(tmp), _stream())
+                first_pos[:, m, :] = tmp
+        keep = return_vertices or return_sq
+        per_item = k * 2 * max_pts * 4 * (2 if return_sq else 1)
+        chunk = n if keep else max(1, min(n, CONTOUR_CHUNK_BYTES // per_item))
+        parts = []
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            parts.append(_contour_chunk(yt[s:e], yp[s:e], k, first_pos[s:e], max_pts, return_vertices, return_sq))
+        if len(parts) == 1:
+            out = parts[0]
+        else:
+            cat = lambda f: torch.cat([getattr(p, f) for p in parts])      # noqa: E731
+            out = ContourOut(cat("n_pts"), cat("flags"), cat("max_sq"), cat("p95_sq"), cat("sum_dist"), None, None,
+                             max_pts)
+        # retry the (rare) items whose contour overflowed max_pts
+        over = ((out.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0).any(dim=1)
+        if bool(over.any()):
+            if keep:
+                raise _lib.OctmError(f"a contour has more than max_pts={max_pts} vertices; raise max_pts")
+            idx = torch.nonzero(over).flatten()
+            big = MAX_MAX_PTS
+            redo = _contour_chunk(yt[idx].contiguous(), yp[idx].contiguous(), k, first_pos[idx].contiguous(), big,
+                                  False, False)
+            still = (redo.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0
+            if bool(still.any()):
+                raise _lib.OctmError(f"a contour has more than {big} vertices: not supported by the "
+                                     "shared-memory distance kernel")
+            for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist"):
+                getattr(out, f)[idx] = getattr(redo, f)
+    return out
+
+
+@dataclass
+class SuiteResult:
+    """Everything one evaluation produced, still on the device; ``metrics()`` brings it to the host."""
+    num_items: int
+    labels: LabelPassOut
+    contours: ContourOut | None
+    _host: dict | None = field(default=None, repr=False)
+
+    def integers(self):
+        """Host copies of the exact integer outputs (numpy; u64/u32 reinterpreted)."""
+        lp, ct = self.labels, self.contours
+        d = {}
+        if lp.counts is not None:
+            d["confusion"] = lp.counts.cpu().numpy().view(np.uint64)
+        if lp.thick_absdiff is not None:
+            d["thickness_absdiff"] = lp.thick_absdiff.cpu().numpy()
+            d["boundary_sq"] = lp.bnd_sq.cpu().numpy()
+            d["boundary_abs"] = lp.bnd_abs.cpu().numpy()
+        if lp.bnd_true is not None:
+            d["boundary_true"] = lp.bnd_true.cpu().numpy()
+            d["boundary_pred"] = lp.bnd_pred.cpu().numpy()
+        if lp.first_pos is not None:
+            d["first_pos"] = lp.first_pos.cpu().numpy().view(np.uint32)
+        if ct is not None:
+            d["contour_n_pts"] = ct.n_pts.cpu().numpy().view(np.uint32)
+            d["contour_flags"] = ct.flags.cpu().numpy().view(np.uint32)
+            d["contour_max_sq"] = ct.max_sq.cpu().numpy().view(np.uint32)
+            d["contour_p95_sq"] = ct.p95_sq.cpu().numpy().view(np.uint32)
+            d["contour_sum_dist"] = ct.sum_dist.cpu().numpy()
+        return d
+
+    def metrics(self):
+        """float64 ``[N, K]`` (``[N, K-1]`` for boundary errors) arrays keyed by reference function name."""
+        if self._host is None:
+            ints = self.integers()
+            m = {}
+            if "confusion" in ints:
+                m.update(derive.count_metrics(*derive.class_counts(ints["confusion"])))
+            if "thickness_absdiff" in ints:
+                m["thickness_difference"] = derive.thickness_difference(ints["thickness_absdiff"], self.labels.width)
+                m.update(derive.boundary_errors(ints["boundary_sq"], ints["boundary_abs"], self.labels.width))
+            if "contour_n_pts" in ints:
+                m.update(derive.contour_metrics(ints["contour_n_pts"], ints["contour_max_sq"],
+                                                ints["contour_p95_sq"], ints["contour_sum_dist"]))
+            self._host = m
+        return self._host
+
+
+def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS):
+    """The full suite on a batch of label maps: fused label pass, then the contour kernels."""
+    yt, yp = _check_pair(y_true, y_pred)
+    lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries)
+    ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts) if contours else None
+    return SuiteResult(yt.shape[0], lp, ct)
+
+
+def validate_labels(labels, num_classes):
+    """Raise ValueError if any label is >= num_classes (one reduction kernel + a 4-byte readback)."""
+    t = (labels.view(torch.uint8) if labels.dtype == torch.bool else labels).contiguous()
+    out = torch.zeros(1, dtype=torch.int32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.call("octm_validate_labels_u8", _ptr(t), t.numel(), _ptr(out), _stream())
+    mx = int(out.item())
+    if mx >= num_classes:
+        raise ValueError(f"label {mx} >= num_classes {num_classes}")

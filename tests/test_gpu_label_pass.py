@@ -1,0 +1,134 @@
+"""GPU parity: fused label pass (K1 + K2 + K3 + seeds) against the oracle -- bit-exact integers."""
+import numpy as np
+import pytest
+
+from oracle import labelmap_oracle as lo
+from retinal_oct_image_segmentation_via_deep_learning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _first_pos_oracle(lab, k):
+    flat = lab.reshape(lab.shape[0], -1)
+    out = np.full((lab.shape[0], k), 0xFFFFFFFF, np.uint32)
+    for i in range(lab.shape[0]):
+        for c in range(k):
+            idx = np.flatnonzero(flat[i] == c)
+            if idx.size:
+                out[i, c] = idx[0]
+    return out
+
+
+def _run(yt, yp, k, cuda, boundaries=True):
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import suite
+    t, p = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+    out = suite.label_pass(t, p, k, counts=True, columns=True, seeds=True, boundaries=boundaries)
+    torch.cuda.synchronize()
+    return out
+
+
+def _check(yt, yp, k, cuda):
+    out = _run(yt, yp, k, cuda)
+    n = yt.shape[0]
+    ref = [lo.score_bscan_fast(yt[i], yp[i], k) for i in range(n)]
+    np.testing.assert_array_equal(out.counts.cpu().numpy().view(np.uint64), np.stack([r["confusion"] for r in ref]))
+    np.testing.assert_array_equal(out.thick_absdiff.cpu().numpy(), np.stack([r["thickness_absdiff"] for r in ref]))
+    np.testing.assert_array_equal(out.bnd_sq.cpu().numpy(), np.stack([r["boundary_sq"] for r in ref]))
+    np.testing.assert_array_equal(out.bnd_abs.cpu().numpy(), np.stack([r["boundary_abs"] for r in ref]))
+    np.testing.assert_array_equal(out.bnd_true.cpu().numpy(), np.stack([r["boundary_true"] for r in ref]))
+    np.testing.assert_array_equal(out.bnd_pred.cpu().numpy(), np.stack([r["boundary_pred"] for r in ref]))
+    fp = out.first_pos.cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(fp[:, 0], _first_pos_oracle(yt, k))
+    np.testing.assert_array_equal(fp[:, 1], _first_pos_oracle(yp, k))
+
+
+def test_golden_suite(cuda, golden_dir):
+    g = np.load(f"{golden_dir}/suite_golden.npz")
+    for name in g["names"]:
+        yt, yp, k = g[f"{name}/y_true"], g[f"{name}/y_pred"], int(g[f"{name}/K"])
+        out = _run(yt, yp, k, cuda)
+        np.testing.assert_array_equal(out.counts.cpu().numpy().view(np.uint64), g[f"{name}/confusion"], err_msg=name)
+        np.testing.assert_array_equal(out.thick_absdiff.cpu().numpy(), g[f"{name}/thickness_absdiff"], err_msg=name)
+        np.testing.assert_array_equal(out.bnd_sq.cpu().numpy(), g[f"{name}/boundary_sq"], err_msg=name)
+        np.testing.assert_array_equal(out.bnd_abs.cpu().numpy(), g[f"{name}/boundary_abs"], err_msg=name)
+        np.testing.assert_array_equal(out.bnd_true.cpu().numpy(), g[f"{name}/boundary_true"], err_msg=name)
+        np.testing.assert_array_equal(out.bnd_pred.cpu().numpy(), g[f"{name}/boundary_pred"], err_msg=name)
+
+
+@pytest.mark.parametrize("shape", [(3, 496, 512, 8), (2, 496, 768, 8), (2, 62, 128, 5), (5, 37, 64, 3),
+                                   (1, 1, 16, 2), (2, 3, 2048, 7), (1, 1030, 256, 8), (3, 128, 144, 4)])
+def test_fast_kernel_layered_and_random(cuda, shape):
+    """Shapes the TMA-staged kernel takes (W % 16 == 0, K <= 8): layered + salt noise, and uniform random."""
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib
+    n, h, w, k = shape
+    assert _lib.load().octm_label_pass_path(h, w, k, 0, 0) == 1
+    if h >= 16:
+        yt, yp = synth.layered_pair(n, h, w, k, seed=h * w + k, noise=0.03, min_gap=1)
+        _check(yt, yp, k, cuda)
+    yt, yp = synth.random_pair(n, h, w, k, seed=7 * h + w)
+    _check(yt, yp, k, cuda)
+
+
+@pytest.mark.parametrize("shape", [(2, 33, 50, 16), (3, 17, 23, 2), (1, 496, 1024, 10), (2, 5, 7, 9), (1, 1, 1, 2),
+                                   (2, 64, 96, 11)])
+def test_generic_kernel(cuda, shape):
+    """Ragged widths and K > 8 go through the generic kernel."""
+    n, h, w, k = shape
+    yt, yp = synth.random_pair(n, h, w, k, seed=h + 31 * w)
+    _check(yt, yp, k, cuda)
+    if h >= 32:
+        yt, yp = synth.layered_pair(n, h, w, k, seed=h * w, noise=0.02, min_gap=1)
+        _check(yt, yp, k, cuda)
+
+
+def test_many_items_persistent_grid(cuda):
+    """More items than resident CTAs: the persistent loop and the ring must stay in step across items."""
+    yt, yp = synth.layered_pair(700, 40, 64, 6, seed=99, noise=0.05, min_gap=1)
+    _check(yt, yp, 6, cuda)
+
+
+def test_uniform_and_absent_classes(cuda):
+    """All-one-class maps and classes that never occur (first_pos = NO_SEED, zero rows in cm)."""
+    yt = np.zeros((2, 24, 32), np.uint8)
+    yp = np.full((2, 24, 32), 3, np.uint8)
+    yt[1, 5:9, 3:20] = 2
+    _check(yt, yp, 5, cuda)
+
+
+def test_standalone_confusion_any_shape(cuda):
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import suite
+    rng = np.random.default_rng(3)
+    for shape, k in [((4, 253952), 8), ((3, 1000), 16), ((2, 7, 9, 11), 4), ((5, 4096), 2)]:
+        a = rng.integers(0, k, size=shape, dtype=np.uint8)
+        b = rng.integers(0, k, size=shape, dtype=np.uint8)
+        cm = suite.confusion(torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda), k).cpu().numpy()
+        for i in range(shape[0]):
+            np.testing.assert_array_equal(cm[i].astype(np.uint64), lo.confusion_matrix(a[i], b[i], k))
+
+
+def test_boundary_error_kernel(cuda):
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import suite
+    rng = np.random.default_rng(4)
+    bt = rng.integers(0, 496, size=(6, 9, 1024), dtype=np.int32)
+    bp = bt + rng.integers(-7, 8, size=bt.shape, dtype=np.int32)
+    sq, ab = suite.boundary_error(torch.from_numpy(bt).to(cuda), torch.from_numpy(bp).to(cuda))
+    d = bt.astype(np.int64) - bp
+    np.testing.assert_array_equal(sq.cpu().numpy(), (d * d).sum(-1))
+    np.testing.assert_array_equal(ab.cpu().numpy(), np.abs(d).sum(-1))
+
+
+def test_derived_ratios_match_oracle(cuda):
+    """float64 ratios from GPU counts vs the per-class reference-style oracle: 1e-6 relative (0 ulp expected)."""
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import suite
+    yt, yp = synth.layered_pair(2, 96, 128, 6, seed=5, noise=0.02)
+    res = suite.evaluate(torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda), 6, contours=False)
+    m = res.metrics()
+    for i in range(2):
+        ref = lo.score_bscan(yt[i], yp[i], 6, contours=False)
+        for name in lo.COUNT_METRICS + ("thickness_difference", "boundary_mse", "boundary_rmse", "boundary_mad"):
+            np.testing.assert_allclose(m[name][i], ref[name], rtol=1e-6, atol=0, err_msg=name)
+            assert np.array_equal(m[name][i], ref[name]), name      # in practice bit-identical
