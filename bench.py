@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""Benchmark: B-scans/s of the full metric suite on synthetic 496x512 8-class label maps (cfg4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--items M]
+
+A "step" is one pass of the whole suite (fused label pass + contour trace + contour distances)
+over this rank's batch of B-scans, inputs resident in HBM.  One process per GPU (torchrun for N>1),
+B-scans are sharded across ranks with no data-path collective (weak scaling: --items per GPU); a
+single small NCCL all-reduce merges the per-class counts for the dataset-level numbers and is part
+of the timed step.  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference's CPU path (the numpy oracle port of Metrics/*.py, per-class
+per-function Python loops, all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, K = 496, 512, 8
+BYTES_PER_BSCAN = 2 * H * W                      # algorithmic (compulsory) label bytes, SURVEY.md 8(d)
+WORKLOAD = "cfg4: full metric suite, synthetic layered 496x512 B-scans, 8 classes"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def _cpu_one(args):
+    seed, contours = args
+    from oracle import labelmap_oracle as lo
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import synth
+    yt, yp = synth.layered_pair(1, H, W, K, seed=seed)
+    t0 = time.perf_counter()
+    lo.score_bscan(yt[0], yp[0], K, contours=contours)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(n_scans, cores, contours=True):
+    """Oracle port of the reference (per-class, per-function numpy calls) on `cores` processes."""
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if cores == 1:
+        per = [_cpu_one((5000 + i, contours)) for i in range(n_scans)]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            per = pool.map(_cpu_one, [(5000 + i, contours) for i in range(n_scans)])
+    wall = time.perf_counter() - t0
+    return n_scans / wall, sum(per) / len(per)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_scans = max(cores, 1)                      # one B-scan per core per step (~10-20 s of CPU work)
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_baseline(min(cores, n_scans), cores)
+    t0 = time.perf_counter()
+    rates = [cpu_baseline(n_scans, cores)[0] for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = n_scans * args.steps / wall
+    sample = f"{n_scans} B-scans per step (one per core), {args.steps} steps, full suite incl. contour metrics"
+    print(json.dumps({
+        "impl": "reference", "metric": "bscans_per_sec_full_metric_suite", "value": value, "unit": "B-scans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "height": H, "width": W, "num_classes": K},
+        "cpu_baseline": {"value": value, "unit": "B-scans/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "B-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "per_step_rates": rates,
+    }))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib, suite, synth
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import dist as odist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    n = args.items
+    yt, yp = synth.layered_pair_device(n, H, W, K, seed=4004 + rank, device=dev)
+    torch.cuda.synchronize()
+
+    timers = {}
+
+    def step():
+        res = suite.evaluate(yt, yp, K, contours=not args.no_contours, timers=timers)
+        tot = odist.dataset_totals(res, world)          # one small all-reduce (no-op for world == 1)
+        return res, tot
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    timers.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res, tot = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * args.steps / (ms / 1e3)
+
+    # per-kernel device times (CUDA events on the launch stream, inside the timed region)
+    kern = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in timers.items()}
+    peak, peak_src = _peaks()
+    lp_ms = kern.get("label_pass")
+    roofline = None
+    if lp_ms:
+        achieved = n * BYTES_PER_BSCAN / (lp_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "label_pass_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": n * BYTES_PER_BSCAN, "ms_per_launch": lp_ms,
+                    "suite_compulsory_gbs_per_gpu": n * BYTES_PER_BSCAN * args.steps / (ms / 1e3) / 1e9}
+
+    # end to end through the public host-array API: pinned host buffers, H2D inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        m = min(n, args.e2e_items)
+        ht, hp = yt[:m].cpu().pin_memory(), yp[:m].cpu().pin_memory()
+        for _ in range(max(1, min(args.warmup, 2))):
+            suite.evaluate_host(ht, hp, K, contours=not args.no_contours, device=dev).metrics()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        d2h = 0
+        for _ in range(e2e_steps):
+            r = suite.evaluate_host(ht, hp, K, contours=not args.no_contours, device=dev)
+            d2h = sum(v.nbytes for v in r.integers().values())
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * m * e2e_steps / float(t.item()), "unit": "B-scans/s",
+               "h2d_bytes_per_step": int(m * BYTES_PER_BSCAN), "d2h_bytes_per_step": int(d2h),
+               "items_per_step_per_gpu": m, "steps": e2e_steps}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            ns = max(1, min(cores, 64))
+            rate, per = cpu_baseline(ns, min(cores, ns))
+            cpu = {"value": rate, "unit": "B-scans/s", "cores": min(cores, ns), "kind": "port",
+                   "sample": f"{ns} B-scans of the same workload, oracle port of Metrics/*.py called per class "
+                             f"per function; {per:.1f} s per B-scan per core"}
+        print(json.dumps({
+            "metric": "bscans_per_sec_full_metric_suite", "value": value, "unit": "B-scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "items_per_gpu": n, "height": H, "width": W, "num_classes": K,
+                       "contours": not args.no_contours, "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2"
+                       % (n * BYTES_PER_BSCAN / 1e9), "sharding": f"items x{world}, one NCCL all-reduce of totals"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "kernel_ms_per_step": kern,
+            "dataset_dice": [float(x) for x in tot["dice_coefficient"]] if tot else None,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--items", type=int, default=16384, help="B-scans per GPU per step")
+    ap.add_argument("--e2e-items", type=int, default=4096)
+    ap.add_argument("--no-contours", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,111 @@
+"""Multi-GPU sharding: one process per GPU, B-scans partitioned contiguously, ONE small all-reduce.
+
+Every reference function is a pure function of one (y_true, y_pred) pair, so items shard with no
+data-path collective.  What crosses NVLink is a packed float64 vector of a few
+hundred bytes per rank: summed confusion counts, column-scan sums, per-class sums of the contour
+metrics and their valid-item counts.  Integer partials ride in float64 exactly (each must stay
+below 2**53, which is checked), so the totals are identical for every world size; the genuine
+floating-point sums differ by rounding only (<= 1e-12 relative).  ``want_max=True`` adds a second
+(MAX) all-reduce for the dataset-level Hausdorff maximum.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import derive
+
+_EXACT_LIMIT = float(2 ** 53)
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous [start, stop) of the items rank `rank` scores; sizes differ by at most one."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def local_partials(ints, metrics, num_classes):
+    """Pack this rank's sums into one float64 vector (layout mirrored by ``unpack``)."""
+    k = num_classes
+    parts = [np.asarray([ints["confusion"].shape[0]], np.float64),
+             ints["confusion"].astype(np.int64).sum(0).reshape(-1).astype(np.float64)]
+    if "thickness_absdiff" in ints:
+        parts += [ints["thickness_absdiff"].sum(0).astype(np.float64),
+                  ints["boundary_sq"].sum(0).astype(np.float64), ints["boundary_abs"].sum(0).astype(np.float64)]
+    else:
+        parts += [np.zeros(k), np.zeros(k - 1), np.zeros(k - 1)]
+    if "contour_valid" in metrics:
+        valid = metrics["contour_valid"]
+        parts.append(valid.sum(0).astype(np.float64))
+        for name in ("hausdorff_distance", "hausdorff_distance_95", "assd"):
+            parts.append(np.where(valid, metrics[name], 0.0).sum(0))
+    else:
+        parts += [np.zeros(k)] * 4
+    vec = np.concatenate(parts)
+    n_exact = 1 + k * k + k + 2 * (k - 1) + k
+    if np.any(np.abs(vec[:n_exact]) >= _EXACT_LIMIT):
+        raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")
+    return vec
+
+
+def unpack(vec, num_classes, width):
+    k = num_classes
+    o = 0
+
+    def take(m):
+        nonlocal o
+        out = vec[o:o + m]
+        o += m
+        return out
+
+    n_items = int(round(take(1)[0]))
+    cm = np.rint(take(k * k)).astype(np.int64).reshape(k, k)
+    thick = np.rint(take(k)).astype(np.int64)
+    bsq, bab = np.rint(take(k - 1)).astype(np.int64), np.rint(take(k - 1)).astype(np.int64)
+    nvalid = np.rint(take(k)).astype(np.int64)
+    s_hd, s_hd95, s_assd = take(k), take(k), take(k)
+    out = {"n_items": n_items, "confusion": cm, "contour_items": nvalid}
+    out.update(derive.count_metrics(*derive.class_counts(cm)))          # pooled (micro) ratios per class
+    denom = max(n_items, 1) * width
+    out["thickness_difference"] = thick.astype(np.float64) / denom       # mean over all columns of all items
+    out["boundary_mse"] = bsq.astype(np.float64) / denom
+    out["boundary_rmse"] = np.sqrt(out["boundary_mse"])
+    out["boundary_mad"] = bab.astype(np.float64) / denom
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out["hausdorff_distance_mean"] = s_hd / nvalid
+        out["hausdorff_distance_95_mean"] = s_hd95 / nvalid
+        out["assd_mean"] = s_assd / nvalid
+    return out
+
+
+def all_reduce_sum(vec, world, device=None, group=None):
+    """float64 SUM all-reduce of a small numpy vector (NCCL on `device`, gloo when device is None/cpu)."""
+    if world == 1:
+        return vec
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(vec))
+    if device is not None and str(device) != "cpu":
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def dataset_totals(res, world, device=None, group=None, want_max=False):
+    """Dataset-level numbers over all ranks' shards from one SuiteResult per rank."""
+    ints, metrics = res.integers(), res.metrics()
+    k, w = res.labels.num_classes, res.labels.width
+    if device is None and world > 1:
+        device = res.labels.counts.device
+    vec = all_reduce_sum(local_partials(ints, metrics, k), world, device, group)
+    out = unpack(vec, k, w)
+    if want_max and "hausdorff_distance" in metrics:
+        local = np.nanmax(np.where(metrics["contour_valid"], metrics["hausdorff_distance"], -np.inf), axis=0)
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(local).to(device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            local = t.cpu().numpy()
+        out["hausdorff_distance_max"] = local
+    return out

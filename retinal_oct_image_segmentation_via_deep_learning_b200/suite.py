@@ -65,7 +65,26 @@ class LabelPassOut:
     first_pos: torch.Tensor | None = None       # [N, 2, K]  uint32 bits
 
 
-def label_pass(y_true, y_pred, num_classes, *, counts=True, columns=True, seeds=False, boundaries=False):
+class _Timed:
+    """Bracket a launch with CUDA events on the current stream when a timers dict is supplied."""
+
+    def __init__(self, timers, key):
+        self.timers, self.key = timers, key
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.timers is not None:
+            self.b.record()
+            self.timers.setdefault(self.key, []).append((self.a, self.b))
+
+
+def label_pass(y_true, y_pred, num_classes, *, counts=True, columns=True, seeds=False, boundaries=False,
+               timers=None):
     """One read of both label tensors -> confusion matrices, column-scan sums, contour seeds."""
     yt, yp = _check_pair(y_true, y_pred)
     n, h, w = yt.shape
@@ -84,9 +103,10 @@ def label_pass(y_true, y_pred, num_classes, *, counts=True, columns=True, seeds=
             out.bnd_pred = torch.empty((n, k - 1, w), dtype=torch.int32, device=dev)
         if seeds:
             out.first_pos = torch.empty((n, 2, k), dtype=torch.int32, device=dev)
-        _lib.call("octm_label_pass_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(out.counts), _ptr(out.thick_absdiff),
-                  _ptr(out.bnd_sq), _ptr(out.bnd_abs), _ptr(out.bnd_true), _ptr(out.bnd_pred), _ptr(out.first_pos),
-                  _stream())
+        with _Timed(timers, "label_pass"):
+            _lib.call("octm_label_pass_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(out.counts),
+                      _ptr(out.thick_absdiff), _ptr(out.bnd_sq), _ptr(out.bnd_abs), _ptr(out.bnd_true),
+                      _ptr(out.bnd_pred), _ptr(out.first_pos), _stream())
     return out
 
 
@@ -134,7 +154,7 @@ class ContourOut:
     max_pts: int = 0
 
 
-def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq):
+def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None):
     n, h, w = yt.shape
     dev = yt.device
     i32 = dict(dtype=torch.int32, device=dev)
@@ -145,15 +165,17 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq):
     p95 = torch.empty((n, k, 2, 2), **i32)
     sums = torch.empty((n, k, 2), dtype=torch.float64, device=dev)
     sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else None
-    _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), max_pts, _ptr(verts),
-              _ptr(n_pts), _ptr(flags), _stream())
-    _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, _ptr(max_sq), _ptr(p95),
-              _ptr(sums), _ptr(sq), _stream())
+    with _Timed(timers, "contour_trace"):
+        _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), max_pts, _ptr(verts),
+                  _ptr(n_pts), _ptr(flags), _stream())
+    with _Timed(timers, "contour_distance"):
+        _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, _ptr(max_sq), _ptr(p95),
+                  _ptr(sums), _ptr(sq), _stream())
     return ContourOut(n_pts, flags, max_sq, p95, sums, verts if want_verts else None, sq, max_pts)
 
 
 def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
-                 return_sq=False):
+                 return_sq=False, timers=None):
     """Contour ``[0]`` of every class mask of both maps, then hausdorff / hd95 / assd integers.
 
     Items are processed in chunks so the vertex workspace stays under ~1 GiB; items whose contour is
@@ -177,7 +199,7 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
         parts = []
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            parts.append(_contour_chunk(yt[s:e], yp[s:e], k, first_pos[s:e], max_pts, return_vertices, return_sq))
+            parts.append(_contour_chunk(yt[s:e], yp[s:e], k, first_pos[s:e], max_pts, return_vertices, return_sq, timers))
         if len(parts) == 1:
             out = parts[0]
         else:
@@ -250,12 +272,90 @@ class SuiteResult:
         return self._host
 
 
-def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS):
-    """The full suite on a batch of label maps: fused label pass, then the contour kernels."""
+def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS, timers=None):
+    """The full suite on a batch of label maps: fused label pass, then the contour kernels.
+
+    ``timers``: optional dict filled with (start, end) CUDA-event pairs per kernel family."""
     yt, yp = _check_pair(y_true, y_pred)
-    lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries)
-    ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts) if contours else None
+    lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries,
+                    timers=timers)
+    ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts, timers=timers) if contours else None
     return SuiteResult(yt.shape[0], lp, ct)
+
+
+def _cat_results(parts):
+    def cat(objs, f):
+        vals = [getattr(o, f) for o in objs]
+        return None if vals[0] is None else torch.cat(vals)
+    lps = [p.labels for p in parts]
+    lp = LabelPassOut(lps[0].num_classes, lps[0].height, lps[0].width,
+                      *[cat(lps, f) for f in ("counts", "thick_absdiff", "bnd_sq", "bnd_abs", "bnd_true", "bnd_pred",
+                                              "first_pos")])
+    ct = None
+    if parts[0].contours is not None:
+        cts = [p.contours for p in parts]
+        ct = ContourOut(*[cat(cts, f) for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist")], None, None,
+                        cts[0].max_pts)
+    return SuiteResult(sum(p.num_items for p in parts), lp, ct)
+
+
+def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, chunk_items=None,
+                  max_pts=DEFAULT_MAX_PTS):
+    """The full suite on HOST label maps (numpy arrays or CPU torch tensors, ideally pinned).
+
+    Items are streamed to the GPU in chunks through two staging buffers: the host->device copy of
+    chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream).  Results stay on the
+    device until ``metrics()`` / ``integers()`` reads them back."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("a CUDA device is required: this package has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    to_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))   # noqa: E731
+    ht, hp = to_t(y_true), to_t(y_pred)
+    if ht.is_cuda or hp.is_cuda:
+        raise TypeError("evaluate_host takes host arrays; use evaluate() for CUDA tensors")
+    if ht.dtype == torch.bool:
+        ht, hp = ht.view(torch.uint8), hp.view(torch.uint8)
+    if ht.dtype != torch.uint8 or hp.dtype != torch.uint8:
+        raise TypeError("label maps must be uint8")
+    if ht.shape != hp.shape or ht.dim() != 3:
+        raise ValueError("expected two [N, H, W] arrays of equal shape")
+    n, h, w = ht.shape
+    if chunk_items is None:
+        chunk_items = max(1, min(n, (256 << 20) // max(1, h * w)))       # ~256 MiB per map per buffer
+    with torch.cuda.device(dev):
+        compute = torch.cuda.current_stream()
+        copy = torch.cuda.Stream()
+        bufs = [(torch.empty((chunk_items, h, w), dtype=torch.uint8, device=dev),
+                 torch.empty((chunk_items, h, w), dtype=torch.uint8, device=dev)) for _ in range(2)]
+        freed = [None, None]
+        starts = list(range(0, n, chunk_items))
+        ready = {}
+
+        def issue_copy(ci):
+            s0, e0 = starts[ci], min(n, starts[ci] + chunk_items)
+            bt, bp = bufs[ci & 1]
+            with torch.cuda.stream(copy):
+                if freed[ci & 1] is not None:
+                    copy.wait_event(freed[ci & 1])               # kernels of chunk ci-2 are done with it
+                bt[:e0 - s0].copy_(ht[s0:e0], non_blocking=True)
+                bp[:e0 - s0].copy_(hp[s0:e0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            ready[ci] = ev
+
+        parts = []
+        issue_copy(0)
+        for ci, s0 in enumerate(starts):
+            e0 = min(n, s0 + chunk_items)
+            if ci + 1 < len(starts):
+                issue_copy(ci + 1)                               # overlaps the kernels launched below
+            bt, bp = bufs[ci & 1]
+            compute.wait_event(ready.pop(ci))
+            parts.append(evaluate(bt[:e0 - s0], bp[:e0 - s0], num_classes, contours=contours, max_pts=max_pts))
+            done = torch.cuda.Event()
+            done.record(compute)
+            freed[ci & 1] = done
+        return parts[0] if len(parts) == 1 else _cat_results(parts)
 
 
 def validate_labels(labels, num_classes):
