@@ -201,7 +201,7 @@ def run_b200(args):
         d2h = 0
         for _ in range(e2e_steps):
             r = suite.evaluate_host(ht, hp, K, contours=not args.no_contours, device=dev)
-            d2h = sum(v.nbytes for v in r.integers().values())
+            d2h = sum(v.nbytes for v in r.metrics().values()) + r.totals_host().nbytes
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)

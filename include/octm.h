@@ -149,6 +149,46 @@ OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pt
                             int num_classes, int max_pts, uint32_t* max_sq, uint32_t* p95_sq,
                             double* sum_dist, uint32_t* sq_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Float64 epilogue on the device.  class_metrics[i][c][m] (double [n][K][OCTM_NUM_CLASS_METRICS]) holds
+ * the value the reference function OCTM_M_* returns for the masks (y_true == c, y_pred == c) of
+ * item i, evaluated from the exact integers above with the reference's operation order
+ * (ConfusionMatrix_based_metrics.py:14-62, Region_based_metrics.py:13-60,
+ *  PixelError_based_metrics.py:14-35, Biomarker_based_metrics.py:18-38,
+ *  Contour_based_metrics.py:22,39,56,68-71).  Contour metrics are NaN where a mask has no contour
+ * (the reference raises IndexError) or when n_pts is NULL.
+ *   boundary_metrics double [n][K-1][3] = mean_squared_error, root_mean_squared_error, mad of the
+ *                                         boundary rows b_k (may be NULL)
+ *   totals           double [octm_totals_len(K)] = this batch's dataset-level partial sums in the
+ *                    layout [n_items | cm K*K | thick K | bnd_sq K-1 | bnd_abs K-1 | contour_items K |
+ *                    sum hd K | sum hd95 K | sum assd K | max hd K | OR of contour flags] (may be NULL);
+ *                    integer fields are exact below 2^53; this is the vector the multi-GPU
+ *                    all-reduce sums. */
+#define OCTM_M_ACCURACY 0
+#define OCTM_M_SENSITIVITY 1
+#define OCTM_M_CM_PRECISION 2
+#define OCTM_M_SPECIFICITY 3
+#define OCTM_M_DICE 4
+#define OCTM_M_IOU 5
+#define OCTM_M_REGION_PRECISION 6
+#define OCTM_M_RECALL 7
+#define OCTM_M_MSE 8
+#define OCTM_M_RMSE 9
+#define OCTM_M_MAD 10
+#define OCTM_M_VASCULARITY 11
+#define OCTM_M_THICKNESS_DIFF 12
+#define OCTM_M_HAUSDORFF 13
+#define OCTM_M_HAUSDORFF95 14
+#define OCTM_M_ASSD 15
+#define OCTM_NUM_CLASS_METRICS 16
+
+OCTM_API int octm_totals_len(int num_classes);
+OCTM_API int octm_derive_metrics(const uint64_t* counts, const int64_t* thick_absdiff, const int64_t* bnd_sq,
+                        const int64_t* bnd_abs, const uint32_t* n_pts, const uint32_t* max_sq,
+                        const uint32_t* p95_sq, const double* sum_dist, const uint32_t* contour_flags,
+                        int64_t n_items, int H, int W, int num_classes, double* class_metrics,
+                        double* boundary_metrics, double* totals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

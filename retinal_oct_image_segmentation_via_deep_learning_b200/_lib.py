@@ -15,6 +15,11 @@ LIB_PATH = os.path.join(_PKG, "liboctm.so")
 OK = 0
 NO_SEED = 0xFFFFFFFF
 CF_TRUE_CLOSED, CF_PRED_CLOSED, CF_TRUE_OVERFLOW, CF_PRED_OVERFLOW = 1, 2, 4, 8
+# column order of the device-derived per-class metrics (OCTM_M_* in include/octm.h)
+CLASS_METRICS = ("accuracy", "sensitivity", "cm_precision", "specificity", "dice_coefficient", "iou_score",
+                 "region_precision", "recall", "mean_squared_error", "root_mean_squared_error", "mad",
+                 "vascularity_index", "thickness_difference", "hausdorff_distance", "hausdorff_distance_95", "assd")
+BOUNDARY_METRICS = ("boundary_mse", "boundary_rmse", "boundary_mad")
 
 _c = ctypes
 _P = _c.c_void_p
@@ -37,6 +42,8 @@ SIGNATURES = {
     "octm_first_pos_u8": (_INT, [_P, _I64, _I64, _INT, _P, _P]),
     "octm_contour2d_trace_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _INT, _P, _P, _P, _P]),
     "octm_contour2d_distance": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P, _P]),
+    "octm_totals_len": (_INT, [_INT]),
+    "octm_derive_metrics": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -75,6 +75,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// Same wait for a thread that is expected to wait long (the producer, always a ring ahead): the
+// suspend-time hint parks the thread in hardware instead of spinning on the issue port shared with
+// the consumer warps of its scheduler.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!done);
+}
+
 // L2 eviction policy for data that is read exactly once.
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t pol;

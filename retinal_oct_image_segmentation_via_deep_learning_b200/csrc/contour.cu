@@ -19,6 +19,8 @@
 //                        inner loop is 2 IMAD + 1 IMNMX per pair, 4 queries per thread.
 //   K7  (same CTA)       max, sum of sqrt(D2/4) in float64, and a radix select of the two order
 //                        statistics numpy's linear 95th percentile interpolates between.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "trace_core.h"
 
@@ -202,6 +204,20 @@ __device__ uint32_t block_select(const uint32_t* vals, int m, uint32_t k, uint32
     return prefix;
 }
 
+constexpr int kBox = 16;      // vertices per bounding box (consecutive in trace order => compact)
+constexpr int kSuper = 8;     // boxes per super-box
+
+// squared distance from q to an axis-aligned box {ymin, ymax, xmin, xmax}: exact lower bound of the
+// squared distance to every vertex inside it
+__device__ __forceinline__ int box_lb2(int4 bx, int qy, int qx) {
+    const int dy = max(max(bx.x - qy, qy - bx.y), 0);
+    const int dx = max(max(bx.z - qx, qx - bx.w), 0);
+    return dy * dy + dx * dx;
+}
+
+// PRUNE = false: brute force (every query against every source vertex).
+// PRUNE = true : the same minimum, skipping boxes whose lower bound cannot beat the current best.
+template <bool PRUNE>
 __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t s_hist[256];
@@ -209,8 +225,15 @@ __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams
     __shared__ double s_dscr[8];
     __shared__ uint32_t s_bc[2];
     const int cap = prm.max_pts;
-    int2* pts[2] = {reinterpret_cast<int2*>(dsm), reinterpret_cast<int2*>(dsm) + cap};   // {y<<16|x, y^2+x^2}
-    uint32_t* d2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(cap) * 16);
+    const int capb = (cap + kBox - 1) / kBox, caps = (capb + kSuper - 1) / kSuper;
+    // shared-memory carve-up (offsets, so every access stays an LDS/STS rather than a generic load)
+    int2* const pts0 = reinterpret_cast<int2*>(dsm);                                     // {y<<16|x, y^2+x^2}
+    uint32_t* const d2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(cap) * 16);
+    int4* const boxes0 = reinterpret_cast<int4*>(dsm + static_cast<size_t>(cap) * 20);
+    int4* const sboxes0 = boxes0 + 2 * capb;
+#define PTS(mm) (pts0 + (mm) * cap)
+#define BOXES(mm) (boxes0 + (mm) * capb)
+#define SBOXES(mm) (sboxes0 + (mm) * caps)
 
     for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
         const uint32_t n0 = prm.n_pts[pair * 2 + 0], n1 = prm.n_pts[pair * 2 + 1];
@@ -229,15 +252,75 @@ __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams
             for (int i = threadIdx.x; i < n[mm]; i += kDistThreads) {
                 const uint32_t v = src[i];
                 const int y = v >> 16, x = v & 0xffff;
-                pts[mm][i] = make_int2(static_cast<int>(v), y * y + x * x);
+                PTS(mm)[i] = make_int2(static_cast<int>(v), y * y + x * x);
             }
         }
         __syncthreads();
+        if (PRUNE) {
+            for (int mm = 0; mm < 2; ++mm) {
+                const int nb = (n[mm] + kBox - 1) / kBox;
+                for (int b = threadIdx.x; b < nb; b += kDistThreads) {
+                    int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+                    const int e = min(n[mm], (b + 1) * kBox);
+                    for (int i = b * kBox; i < e; ++i) {
+                        const uint32_t v = static_cast<uint32_t>(PTS(mm)[i].x);
+                        const int y = v >> 16, x = v & 0xffff;
+                        ymin = min(ymin, y); ymax = max(ymax, y); xmin = min(xmin, x); xmax = max(xmax, x);
+                    }
+                    BOXES(mm)[b] = make_int4(ymin, ymax, xmin, xmax);
+                }
+            }
+            __syncthreads();
+            for (int mm = 0; mm < 2; ++mm) {
+                const int nb = (n[mm] + kBox - 1) / kBox, nsb = (nb + kSuper - 1) / kSuper;
+                for (int sb = threadIdx.x; sb < nsb; sb += kDistThreads) {
+                    int4 acc = BOXES(mm)[sb * kSuper];
+                    const int e = min(nb, (sb + 1) * kSuper);
+                    for (int b = sb * kSuper + 1; b < e; ++b) {
+                        const int4 c = BOXES(mm)[b];
+                        acc.x = min(acc.x, c.x); acc.y = max(acc.y, c.y); acc.z = min(acc.z, c.z); acc.w = max(acc.w, c.w);
+                    }
+                    SBOXES(mm)[sb] = acc;
+                }
+            }
+            __syncthreads();
+        }
         // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
         for (int dir = 0; dir < 2; ++dir) {
-            const int2* qs = pts[1 - dir];
-            const int2* ss = pts[dir];
+            const int2* qs = PTS(1 - dir);
+            const int2* ss = PTS(dir);
             const int nq = n[1 - dir], ns = n[dir];
+            if (PRUNE) {
+                const int4* bxs = BOXES(dir);
+                const int4* sbs = SBOXES(dir);
+                const float ratio = static_cast<float>(ns) / static_cast<float>(nq);
+                const int nb = (ns + kBox - 1) / kBox, nsb = (nb + kSuper - 1) / kSuper;
+                for (int j = threadIdx.x; j < nq; j += kDistThreads) {
+                    const int2 q = qs[j];
+                    const int qy = static_cast<uint32_t>(q.x) >> 16, qx = q.x & 0xffff;
+                    const int cy = -2 * qy, cx = -2 * qx;
+                    // prime the bound with the vertex at the same relative position along the other contour
+                    const int2 g = ss[min(ns - 1, static_cast<int>(static_cast<float>(j) * ratio))];
+                    int bm = (g.x & 0xffff) * cx + (static_cast<int>(static_cast<uint32_t>(g.x) >> 16) * cy + g.y);
+                    int bestd = bm + q.y;
+                    for (int sb = 0; sb < nsb; ++sb) {
+                        if (box_lb2(sbs[sb], qy, qx) >= bestd) continue;
+                        const int be = min(nb, (sb + 1) * kSuper);
+                        for (int b = sb * kSuper; b < be; ++b) {
+                            if (box_lb2(bxs[b], qy, qx) >= bestd) continue;
+                            const int e = min(ns, (b + 1) * kBox);
+#pragma unroll 4
+                            for (int i = b * kBox; i < e; ++i) {
+                                const int2 s = ss[i];
+                                const int ay = static_cast<uint32_t>(s.x) >> 16, ax = s.x & 0xffff;
+                                bm = min(bm, ax * cx + (ay * cy + s.y));
+                            }
+                            bestd = bm + q.y;
+                        }
+                    }
+                    d2[j] = static_cast<uint32_t>(bestd);
+                }
+            } else {
             for (int base = 0; base < nq; base += kDistThreads * kQ) {
                 int cy[kQ], cx[kQ], best[kQ], qn[kQ];
 #pragma unroll
@@ -261,6 +344,7 @@ __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams
                     const int j = base + t * kDistThreads + static_cast<int>(threadIdx.x);
                     if (j < nq) d2[j] = static_cast<uint32_t>(best[t] + qn[t]);
                 }
+            }
             }
             __syncthreads();
             // K7: max, sum of sqrt, two order statistics
@@ -342,7 +426,10 @@ extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_p
     return octm::check_launch("trace_kernel");
 }
 
-static size_t dist_smem(int max_pts) { return static_cast<size_t>(max_pts) * 20; }
+static size_t dist_smem(int max_pts) {
+    const size_t capb = (max_pts + octm::kBox - 1) / octm::kBox, caps = (capb + octm::kSuper - 1) / octm::kSuper;
+    return static_cast<size_t>(max_pts) * 20 + 2 * (capb + caps) * 16;
+}
 
 extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
                                        int max_pts, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
@@ -353,14 +440,16 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
     const size_t smem = dist_smem(max_pts);
     if (smem > static_cast<size_t>(octm::max_optin_smem()) - 4096)
         return octm::fail(OCTM_ERR_UNSUPPORTED, "max_pts %d needs %zu B of shared memory", max_pts, smem);
-    if (cudaFuncSetAttribute(octm::distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             octm::max_optin_smem() - 4096) != cudaSuccess)
+    // OCTM_DISTANCE_BRUTE=1 selects the unpruned kernel (A/B checks; both give identical integers)
+    static const bool brute = [] { const char* e = getenv("OCTM_DISTANCE_BRUTE"); return e && e[0] == '1'; }();
+    auto kern = brute ? octm::distance_kernel<false> : octm::distance_kernel<true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, octm::max_optin_smem() - 4096) != cudaSuccess)
         return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
     octm::DistParams p{verts, n_pts, n_items * num_classes, max_pts, max_sq, p95_sq, sum_dist, sq_out};
     long long grid = n_items * num_classes;
     const long long cap = static_cast<long long>(octm::sm_count()) * 16;
     if (grid > cap) grid = cap;
-    octm::distance_kernel<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     return octm::check_launch("distance_kernel");
 }
 

@@ -26,14 +26,17 @@
 //     histograms -> K x K counts, one plain store per output element (no global atomics).
 //
 // GENERIC KERNEL: any H, W, K <= 16 (byte loads, shared-memory atomics).  Same outputs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace octm {
 
 constexpr int kStrip = 128;        // columns per consumer warp
-constexpr int kQueueCap = 64;      // queue entries (8 pixel pairs each) per warp
+constexpr int kQueueCap = 64;      // queue entries (16 pixel pairs each) per warp
 constexpr int kMaxStages = 8;
-constexpr uint32_t kPadWord = 0x08080808u;   // label 8: every PRMT LUT below maps it to 0
+constexpr uint32_t kPadWord = 0x08080808u;   // label 8: PRMT nibble 8 = "replicate sign of LUT byte 0" = 0x00
+constexpr uint32_t kSkipWord = 0xFFFFFFFFu;  // queue marker: this word holds no pixels
 
 struct LabelPassParams {
     const uint8_t* yt;
@@ -61,7 +64,7 @@ constexpr int kOffFirst = kOffThick + 128;     // u32[2][16]
 constexpr int kOffWarp = 2048;
 constexpr int kWarpTotals = 2 * 8 * kStrip * 2;    // u16 [map][thr][128]
 constexpr int kWarpHist = 64 * 32 * 2;             // u16 [code][lane]
-constexpr int kWarpQueue = kQueueCap * 8;          // uint2 entries
+constexpr int kWarpQueue = kQueueCap * 16;         // uint4 entries
 constexpr int kWarpBytes = kWarpTotals + kWarpHist + kWarpQueue;
 
 __host__ __device__ constexpr uint32_t lut_word(int k1, int k2, int v0) {
@@ -74,52 +77,83 @@ __host__ __device__ constexpr uint32_t lut_word(int k1, int k2, int v0) {
     return w;
 }
 
-// labels of 4 pixels (bytes, each < 16) -> PRMT selector with pixel i in nibble i
-__device__ __forceinline__ uint32_t pack_sel(uint32_t x) {
-    uint32_t t = x | (x >> 4);
-    return __byte_perm(t, 0, 0x4420);   // byte0 <- t.b0, byte1 <- t.b2
+// raw PRMT: unlike __byte_perm the selector is not masked to 3 bits per nibble, so nibble value 8
+// (the pad label) selects "sign of byte 0", which is 0x00 for every LUT used here.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 }
 
+// Column-scan state of one lane: 2 word slots x 2 halves; every accumulator byte belongs to one
+// (map, column): byte0 = y_true col a, byte1 = y_pred col a, byte2 = y_true col b, byte3 = y_pred col b,
+// with (a, b) = columns (0, 1) of the word for half 0 and (2, 3) for half 1.
 template <int NP>
 struct ColState {
-    uint32_t nibT[2][NP], nibP[2][NP];
-    uint32_t bytT[2][2 * NP], bytP[2][2 * NP];
+    uint32_t nib[2][2][NP];        // two 4-bit counters per byte: thresholds 2q+1 (low), 2q+2 (high)
+    uint32_t byt[2][2][2 * NP];    // one 8-bit counter per byte: threshold j+1
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int q = 0; q < NP; ++q) nibT[s][q] = nibP[s][q] = 0;
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int j = 0; j < 2 * NP; ++j) bytT[s][j] = bytP[s][j] = 0;
-        }
+                for (int q = 0; q < NP; ++q) nib[s][h][q] = 0;
+#pragma unroll
+                for (int j = 0; j < 2 * NP; ++j) byt[s][h][j] = 0;
+            }
     }
     __device__ __forceinline__ void nib_to_byte() {
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                bytT[s][2 * q] += nibT[s][q] & 0x0f0f0f0fu;
-                bytT[s][2 * q + 1] += (nibT[s][q] >> 4) & 0x0f0f0f0fu;
-                bytP[s][2 * q] += nibP[s][q] & 0x0f0f0f0fu;
-                bytP[s][2 * q + 1] += (nibP[s][q] >> 4) & 0x0f0f0f0fu;
-                nibT[s][q] = nibP[s][q] = 0;
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    byt[s][h][2 * q] += nib[s][h][q] & 0x0f0f0f0fu;
+                    byt[s][h][2 * q + 1] += (nib[s][h][q] >> 4) & 0x0f0f0f0fu;
+                    nib[s][h][q] = 0;
+                }
+    }
+    // add the byte counters into the warp's uint16 column totals [map][thr][128] and clear them
+    __device__ __forceinline__ void byte_to_totals(unsigned short* totals, int lane) {
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {          // the two row phases own the same columns: take turns
+            if ((lane >> 4) == hp) {
+#pragma unroll
+                for (int j = 0; j < 2 * NP; ++j) {
+                    uint4* tt = reinterpret_cast<uint4*>(totals + (0 * 8 + j) * kStrip + (lane & 15) * 8);
+                    uint4* tp = reinterpret_cast<uint4*>(totals + (1 * 8 + j) * kStrip + (lane & 15) * 8);
+                    uint4 a = *tt, b = *tp;
+                    a.x += prmt(byt[0][0][j], 0, 0x4240); b.x += prmt(byt[0][0][j], 0, 0x4341);
+                    a.y += prmt(byt[0][1][j], 0, 0x4240); b.y += prmt(byt[0][1][j], 0, 0x4341);
+                    a.z += prmt(byt[1][0][j], 0, 0x4240); b.z += prmt(byt[1][0][j], 0, 0x4341);
+                    a.w += prmt(byt[1][1][j], 0, 0x4240); b.w += prmt(byt[1][1][j], 0, 0x4341);
+                    *tt = a;
+                    *tp = b;
+                    byt[0][0][j] = byt[0][1][j] = byt[1][0][j] = byt[1][1][j] = 0;
+                }
             }
+            __syncwarp();
+        }
     }
 };
 
-template <int NP>
-__device__ __forceinline__ void col_accumulate(uint32_t (&nib)[2][NP], uint32_t a0, uint32_t a1, uint32_t b0,
-                                               uint32_t b1, uint32_t& pres, bool seeds) {
-    const uint32_t sa[2] = {pack_sel(a0), pack_sel(a1)};
-    const uint32_t sb[2] = {pack_sel(b0), pack_sel(b1)};
+// two rows (A, B) of one word slot: t/p words -> interleaved selector -> LUT flags -> nibble counters
+template <int NP, bool SEEDS>
+__device__ __forceinline__ void col_accumulate(uint32_t (&nib)[2][NP], uint32_t tA, uint32_t pA, uint32_t tB,
+                                               uint32_t pB, uint32_t& pres, bool want_pres) {
+    const uint32_t xa = pA * 16u + tA, xb = pB * 16u + tB;      // nibbles: t0 p0 t1 p1 | t2 p2 t3 p3
+    const uint32_t sel[2][2] = {{xa, xa >> 16}, {xb, xb >> 16}};
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const uint32_t lo = lut_word(2 * q + 1, 2 * q + 2, 0), hi = lut_word(2 * q + 1, 2 * q + 2, 4);
-            nib[s][q] = nib[s][q] + __byte_perm(lo, hi, sa[s]) + __byte_perm(lo, hi, sb[s]);
+            nib[h][q] = nib[h][q] + prmt(lo, hi, sel[0][h]) + prmt(lo, hi, sel[1][h]);
         }
-        if (seeds) pres |= __byte_perm(0x08040201u, 0x80402010u, sa[s]) | __byte_perm(0x08040201u, 0x80402010u, sb[s]);
+        if (SEEDS && want_pres)
+            pres |= prmt(0x08040201u, 0x80402010u, sel[0][h]) | prmt(0x08040201u, 0x80402010u, sel[1][h]);
     }
 }
 
@@ -128,26 +162,24 @@ __device__ __forceinline__ void hist_add(unsigned short* hist_lane, uint32_t cod
     *h = static_cast<unsigned short>(*h + inc);
 }
 
-__device__ __forceinline__ void drain_entry(unsigned short* hist_lane, uint2 e) {
+__device__ __forceinline__ void drain_entry(unsigned short* hist_lane, uint4 e) {
+    const uint32_t w[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) hist_add(hist_lane, (e.x >> (8 * i)) & 0x3fu, 1);
+    for (int k = 0; k < 4; ++k) {
+        if (w[k] != kSkipWord) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) hist_add(hist_lane, (e.y >> (8 * i)) & 0x3fu, 1);
+            for (int i = 0; i < 4; ++i) hist_add(hist_lane, (w[k] >> (8 * i)) & 0x3fu, 1);
+        }
+    }
 }
 
-// one row (8 pixel pairs per lane) into the confusion machinery
-__device__ __forceinline__ void conf_step(uint2 t, uint2 p, bool valid, unsigned short* hist_lane, uint2* queue,
+// confusion machinery for up to two rows (16 pixel pairs) of one lane.  j* are joint-code words
+// (t*8+p per byte) or kSkipWord for rows that do not exist.
+__device__ __forceinline__ void conf_push(bool mixed_lane, uint4 e, unsigned short* hist_lane, uint4* queue,
                                           uint32_t& qhead, uint32_t& qtail, int lane) {
-    const uint32_t j0 = t.x * 8u + p.x, j1 = t.y * 8u + p.y;
-    const uint32_t b = __byte_perm(j0, 0, 0x0000);
-    const bool uni = ((j0 ^ b) | (j1 ^ b)) == 0;
-    if (valid && uni) hist_add(hist_lane, b & 0x3fu, 8);
-    const uint32_t mixed = __ballot_sync(0xffffffffu, valid && !uni);
+    const uint32_t mixed = __ballot_sync(0xffffffffu, mixed_lane);
     if (mixed) {
-        if (valid && !uni) {
-            const uint32_t pos = qtail + __popc(mixed & lanemask_lt());
-            queue[pos & (kQueueCap - 1)] = make_uint2(j0, j1);
-        }
+        if (mixed_lane) queue[(qtail + __popc(mixed & lanemask_lt())) & (kQueueCap - 1)] = e;
         qtail += __popc(mixed);
         __syncwarp();
         if (qtail - qhead >= 32) {
@@ -193,19 +225,19 @@ __global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_p
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
-            uint32_t cnt = 0;
+            uint32_t s = 0, ph = 0;
             for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
                 const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
                 const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
-                for (int r0 = 0; r0 < H; r0 += R, ++cnt) {
+                for (int r0 = 0; r0 < H; r0 += R) {
                     const int rows = min(R, H - r0);
-                    const uint32_t s = cnt % S, ph = (cnt / S) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_wait_parked(&empty[s], ph ^ 1);
                     const uint32_t bytes = static_cast<uint32_t>(rows) * W;
                     mbar_arrive_expect_tx(&full[s], 2 * bytes);
                     uint8_t* dst = ring + static_cast<size_t>(s) * stage_bytes;
                     bulk_g2s(dst, bt + static_cast<long long>(r0) * W, bytes, &full[s], pol);
                     bulk_g2s(dst + map_bytes, bp + static_cast<long long>(r0) * W, bytes, &full[s], pol);
+                    if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -217,95 +249,99 @@ __global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_p
     unsigned short* totals = reinterpret_cast<unsigned short*>(wbase);                       // [2][8][128]
     unsigned short* hist = reinterpret_cast<unsigned short*>(wbase + kWarpTotals);           // [64][32]
     unsigned short* hist_lane = hist + lane;
-    uint2* queue = reinterpret_cast<uint2*>(wbase + kWarpTotals + kWarpHist);
+    uint4* queue = reinterpret_cast<uint4*>(wbase + kWarpTotals + kWarpHist);
     const int phase = lane >> 4;
     const int col = warp * kStrip + (lane & 15) * 8;      // first of this lane's 8 columns
     const bool colv = col < W;
+    const bool strip_full = (warp + 1) * kStrip <= W;      // warp-uniform
     const int nthr = K - 1;
     const int consumers = NW * 32;
+    const uint32_t all_found = ((1u << K) - 1u) * 0x101u;
+    const uint32_t lane_off = static_cast<uint32_t>(phase) * W + col;
 
     ColState<NP> cs;
-    uint32_t cnt = 0;
+    uint32_t s = 0, ph = 0;
     for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
         if (COLS) cs.clear();
         uint32_t qhead = 0, qtail = 0;
         uint32_t found = 0;
         int nib_fill = 0, byt_fill = 0;
 
-        for (int r0 = 0; r0 < H; r0 += R, ++cnt) {
+        for (int r0 = 0; r0 < H; r0 += R) {
             const int rows = min(R, H - r0);
-            const uint32_t s = cnt % S, ph = (cnt / S) & 1;
             mbar_wait(&full[s], ph);
-            const uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes + col;
+            const uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes + lane_off;   // this lane's first row
             const uint8_t* sp = st + map_bytes;
-            uint32_t presT = 0, presP = 0;
+            uint32_t pres = 0;
+            const bool want_pres = SEEDS && found != all_found;
             const int npairs = (rows + 3) >> 2;
-#pragma unroll 2
-            for (int pr = 0; pr < npairs; ++pr) {
-                const int ra = 4 * pr + phase, rb = ra + 2;
-                const bool va = colv && ra < rows, vb = colv && rb < rows;
-                uint2 tA = make_uint2(kPadWord, kPadWord), pA = tA, tB = tA, pB = tA;
-                if (va) {
-                    tA = *reinterpret_cast<const uint2*>(st + ra * W);
-                    pA = *reinterpret_cast<const uint2*>(sp + ra * W);
-                }
-                if (vb) {
-                    tB = *reinterpret_cast<const uint2*>(st + rb * W);
-                    pB = *reinterpret_cast<const uint2*>(sp + rb * W);
-                }
-                if (COLS || SEEDS) {
-                    col_accumulate<NP>(cs.nibT, tA.x, tA.y, tB.x, tB.y, presT, SEEDS);
-                    col_accumulate<NP>(cs.nibP, pA.x, pA.y, pB.x, pB.y, presP, SEEDS);
+            if (strip_full && (rows & 3) == 0) {
+                // -------- every lane has both of its rows: no predicates.  Not unrolled: one pass is
+                // ~140 instructions and must stay inside the 6 KB L0 instruction cache.
+#pragma unroll 1
+                for (int pr = 0; pr < npairs; ++pr) {
+                    const uint2 tA = *reinterpret_cast<const uint2*>(st + (4 * pr) * W);
+                    const uint2 pA = *reinterpret_cast<const uint2*>(sp + (4 * pr) * W);
+                    const uint2 tB = *reinterpret_cast<const uint2*>(st + (4 * pr + 2) * W);
+                    const uint2 pB = *reinterpret_cast<const uint2*>(sp + (4 * pr + 2) * W);
+                    if (COLS || SEEDS) {
+                        col_accumulate<NP, SEEDS>(cs.nib[0], tA.x, pA.x, tB.x, pB.x, pres, want_pres);
+                        col_accumulate<NP, SEEDS>(cs.nib[1], tA.y, pA.y, tB.y, pB.y, pres, want_pres);
+                    }
+                    if (CONF) {
+                        const uint4 j = make_uint4(tA.x * 8u + pA.x, tA.y * 8u + pA.y, tB.x * 8u + pB.x, tB.y * 8u + pB.y);
+                        const uint32_t b = prmt(j.x, 0, 0);
+                        const bool uni = (((j.x ^ b) | (j.y ^ b)) | ((j.z ^ b) | (j.w ^ b))) == 0;
+                        if (uni) hist_add(hist_lane, b & 0x3fu, 16);
+                        conf_push(!uni, j, hist_lane, queue, qhead, qtail, lane);
+                    }
                     if (COLS && ++nib_fill == 7) {
                         cs.nib_to_byte();
                         nib_fill = 0;
-                        if (++byt_fill == 18) {
-                            // byte counters could overflow: spill into the uint16 column totals
-                            byt_fill = 0;
-#pragma unroll
-                            for (int hp = 0; hp < 2; ++hp) {
-                                if (phase == hp && colv) {
-#pragma unroll
-                                    for (int j = 0; j < 2 * NP; ++j) {
-                                        uint4* tt = reinterpret_cast<uint4*>(totals + (0 * 8 + j) * kStrip + (lane & 15) * 8);
-                                        uint4* tp = reinterpret_cast<uint4*>(totals + (1 * 8 + j) * kStrip + (lane & 15) * 8);
-                                        uint4 a = *tt, b = *tp;
-                                        a.x += __byte_perm(cs.bytT[0][j], 0, 0x4140);
-                                        a.y += __byte_perm(cs.bytT[0][j], 0, 0x4342);
-                                        a.z += __byte_perm(cs.bytT[1][j], 0, 0x4140);
-                                        a.w += __byte_perm(cs.bytT[1][j], 0, 0x4342);
-                                        b.x += __byte_perm(cs.bytP[0][j], 0, 0x4140);
-                                        b.y += __byte_perm(cs.bytP[0][j], 0, 0x4342);
-                                        b.z += __byte_perm(cs.bytP[1][j], 0, 0x4140);
-                                        b.w += __byte_perm(cs.bytP[1][j], 0, 0x4342);
-                                        *tt = a;
-                                        *tp = b;
-                                        cs.bytT[0][j] = cs.bytT[1][j] = cs.bytP[0][j] = cs.bytP[1][j] = 0;
-                                    }
-                                }
-                                __syncwarp();
-                            }
-                        }
+                        if (++byt_fill == 18) { byt_fill = 0; cs.byte_to_totals(totals, lane); }
                     }
                 }
-                if (CONF) {
-                    conf_step(tA, pA, va, hist_lane, queue, qhead, qtail, lane);
-                    conf_step(tB, pB, vb, hist_lane, queue, qhead, qtail, lane);
+            } else {
+                // -------- ragged strip or last rows of the item: per-row validity
+                for (int pr = 0; pr < npairs; ++pr) {
+                    const int ra = 4 * pr + phase, rb = ra + 2;
+                    const bool va = colv && ra < rows, vb = colv && rb < rows;
+                    uint2 tA = make_uint2(kPadWord, kPadWord), pA = tA, tB = tA, pB = tA;
+                    if (va) {
+                        tA = *reinterpret_cast<const uint2*>(st + (4 * pr) * W);
+                        pA = *reinterpret_cast<const uint2*>(sp + (4 * pr) * W);
+                    }
+                    if (vb) {
+                        tB = *reinterpret_cast<const uint2*>(st + (4 * pr + 2) * W);
+                        pB = *reinterpret_cast<const uint2*>(sp + (4 * pr + 2) * W);
+                    }
+                    if (COLS || SEEDS) {
+                        col_accumulate<NP, SEEDS>(cs.nib[0], tA.x, pA.x, tB.x, pB.x, pres, want_pres);
+                        col_accumulate<NP, SEEDS>(cs.nib[1], tA.y, pA.y, tB.y, pB.y, pres, want_pres);
+                    }
+                    if (CONF) {
+                        uint4 j = make_uint4(tA.x * 8u + pA.x, tA.y * 8u + pA.y, tB.x * 8u + pB.x, tB.y * 8u + pB.y);
+                        if (!va) j.x = j.y = kSkipWord;
+                        if (!vb) j.z = j.w = kSkipWord;
+                        conf_push(va || vb, j, hist_lane, queue, qhead, qtail, lane);
+                    }
+                    if (COLS && ++nib_fill == 7) {
+                        cs.nib_to_byte();
+                        nib_fill = 0;
+                        if (++byt_fill == 18) { byt_fill = 0; cs.byte_to_totals(totals, lane); }
+                    }
                 }
             }
-            if (SEEDS) {
-                // classes seen in this stage, by map: bits 0-7 y_true, 8-15 y_pred
-                uint32_t mt = presT | (presT >> 16);
-                mt = (mt | (mt >> 8)) & 0xffu;
-                uint32_t mp = presP | (presP >> 16);
-                mp = (mp | (mp >> 8)) & 0xffu;
-                uint32_t fresh = __reduce_or_sync(0xffffffffu, (mt | (mp << 8)) & ~found);
+            if (SEEDS && want_pres) {
+                // classes seen in this stage: bits 0-7 y_true, 8-15 y_pred
+                uint32_t fresh = __reduce_or_sync(0xffffffffu, ((pres | (pres >> 16)) & 0xffffu) & ~found);
                 found |= fresh;
+                const uint8_t* st0 = st - lane_off + col;      // row 0 of the stage, this lane's columns
                 while (fresh) {
                     const int bit = __ffs(fresh) - 1;
                     fresh &= fresh - 1;
                     const int m = bit >> 3, c = bit & 7;
-                    const uint8_t* sm = m ? sp : st;
+                    const uint8_t* sm = m ? st0 + map_bytes : st0;
                     const uint32_t cc = 0x01010101u * c;
                     for (int pp = 0; pp < (rows + 1) / 2; ++pp) {
                         const int rr = 2 * pp + phase;
@@ -327,33 +363,13 @@ __global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_p
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
         }
 
         // ------------------------------------------------------------------ item epilogue
         if (COLS) {
             cs.nib_to_byte();
-#pragma unroll
-            for (int hp = 0; hp < 2; ++hp) {
-                if (phase == hp && colv) {
-#pragma unroll
-                    for (int j = 0; j < 2 * NP; ++j) {
-                        uint4* tt = reinterpret_cast<uint4*>(totals + (0 * 8 + j) * kStrip + (lane & 15) * 8);
-                        uint4* tp = reinterpret_cast<uint4*>(totals + (1 * 8 + j) * kStrip + (lane & 15) * 8);
-                        uint4 a = *tt, b = *tp;
-                        a.x += __byte_perm(cs.bytT[0][j], 0, 0x4140);
-                        a.y += __byte_perm(cs.bytT[0][j], 0, 0x4342);
-                        a.z += __byte_perm(cs.bytT[1][j], 0, 0x4140);
-                        a.w += __byte_perm(cs.bytT[1][j], 0, 0x4342);
-                        b.x += __byte_perm(cs.bytP[0][j], 0, 0x4140);
-                        b.y += __byte_perm(cs.bytP[0][j], 0, 0x4342);
-                        b.z += __byte_perm(cs.bytP[1][j], 0, 0x4140);
-                        b.w += __byte_perm(cs.bytP[1][j], 0, 0x4342);
-                        *tt = a;
-                        *tp = b;
-                    }
-                }
-                __syncwarp();
-            }
+            cs.byte_to_totals(totals, lane);
             // per-column arithmetic: lane owns 4 columns of the strip
             const int lc = lane * 4;
             const bool cv = warp * kStrip + lc < W;
@@ -590,14 +606,18 @@ template <int NP, bool CONF, bool COLS, bool SEEDS>
 static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     LabelPassParams p = p0;
     const int NW = (p.W + kStrip - 1) / kStrip;
-    // rows per stage: ~4 KB per map, multiple of 4; 4 stages in flight per CTA
-    int R = (4096 / p.W) & ~3;
+    // rows per stage: ~6 KB per map (multiple of 4 rows), 3 stages in flight per CTA.
+    // OCTM_LP_ROWS / OCTM_LP_STAGES override for tuning runs.
+    static const int env_rows = [] { const char* e = getenv("OCTM_LP_ROWS"); return e ? atoi(e) : 0; }();
+    static const int env_stages = [] { const char* e = getenv("OCTM_LP_STAGES"); return e ? atoi(e) : 0; }();
+    int R = (6144 / p.W) & ~3;
+    if (env_rows > 0) R = env_rows & ~3;
     if (R < 4) R = 4;
     p.R = R;
     const int fixed = ((kOffWarp + NW * kWarpBytes + 127) & ~127);
     const int stage = 2 * R * p.W;
     const int budget = max_optin_smem();
-    int S = 4;
+    int S = env_stages >= 2 && env_stages <= kMaxStages ? env_stages : 3;
     while (S > 2 && fixed + S * stage > budget) --S;
     p.S = S;
     const int smem = fixed + S * stage;

@@ -19,7 +19,7 @@ import torch
 from . import _lib, derive
 
 DEFAULT_MAX_PTS = 2048       # contour vertices kept per (item, class, map) on the first attempt
-MAX_MAX_PTS = 11000          # shared-memory bound of the distance kernel (20 B per vertex)
+MAX_MAX_PTS = 10000          # shared-memory bound of the distance kernel (~22.3 B per vertex)
 CONTOUR_CHUNK_BYTES = 1 << 30
 
 
@@ -175,7 +175,7 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
 
 
 def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
-                 return_sq=False, timers=None):
+                 return_sq=False, timers=None, check_overflow=True):
     """Contour ``[0]`` of every class mask of both maps, then hausdorff / hd95 / assd integers.
 
     Items are processed in chunks so the vertex workspace stays under ~1 GiB; items whose contour is
@@ -206,34 +206,83 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
             cat = lambda f: torch.cat([getattr(p, f) for p in parts])      # noqa: E731
             out = ContourOut(cat("n_pts"), cat("flags"), cat("max_sq"), cat("p95_sq"), cat("sum_dist"), None, None,
                              max_pts)
-        # retry the (rare) items whose contour overflowed max_pts
-        over = ((out.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0).any(dim=1)
-        if bool(over.any()):
-            if keep:
-                raise _lib.OctmError(f"a contour has more than max_pts={max_pts} vertices; raise max_pts")
-            idx = torch.nonzero(over).flatten()
-            big = MAX_MAX_PTS
-            redo = _contour_chunk(yt[idx].contiguous(), yp[idx].contiguous(), k, first_pos[idx].contiguous(), big,
-                                  False, False)
-            still = (redo.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0
-            if bool(still.any()):
-                raise _lib.OctmError(f"a contour has more than {big} vertices: not supported by the "
-                                     "shared-memory distance kernel")
-            for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist"):
-                getattr(out, f)[idx] = getattr(redo, f)
+        if check_overflow:
+            _retry_overflow(out, yt, yp, k, first_pos, keep)
     return out
+
+
+def _retry_overflow(out, yt, yp, k, first_pos, keep=False):
+    """Re-run, with the largest vertex bound, the (rare) items whose contour overflowed ``max_pts``.
+    Returns True when something was redone.  Costs one device->host sync."""
+    over = ((out.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0).any(dim=1)
+    if not bool(over.any()):
+        return False
+    if keep:
+        raise _lib.OctmError(f"a contour has more than max_pts={out.max_pts} vertices; raise max_pts")
+    idx = torch.nonzero(over).flatten()
+    big = MAX_MAX_PTS
+    redo = _contour_chunk(yt[idx].contiguous(), yp[idx].contiguous(), k, first_pos[idx].contiguous(), big, False, False)
+    still = (redo.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0
+    if bool(still.any()):
+        raise _lib.OctmError(f"a contour has more than {big} vertices: not supported by the "
+                             "shared-memory distance kernel")
+    for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist"):
+        getattr(out, f)[idx] = getattr(redo, f)
+    return True
+
+
+def derive_on_device(lp, ct, n, timers=None):
+    """Float64 per-class metrics + this batch's dataset totals, computed by ``octm_derive_metrics``."""
+    k, dev = lp.num_classes, lp.counts.device
+    cls = torch.empty((n, k, len(_lib.CLASS_METRICS)), dtype=torch.float64, device=dev)
+    bnd = torch.empty((n, k - 1, 3), dtype=torch.float64, device=dev) if lp.bnd_sq is not None else None
+    tot = torch.empty((_lib.load().octm_totals_len(k),), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev), _Timed(timers, "derive"):
+        _lib.call("octm_derive_metrics", _ptr(lp.counts), _ptr(lp.thick_absdiff), _ptr(lp.bnd_sq), _ptr(lp.bnd_abs),
+                  _ptr(ct.n_pts) if ct else None, _ptr(ct.max_sq) if ct else None, _ptr(ct.p95_sq) if ct else None,
+                  _ptr(ct.sum_dist) if ct else None, _ptr(ct.flags) if ct else None, n, lp.height, lp.width, k,
+                  _ptr(cls), _ptr(bnd), _ptr(tot), _stream())
+    return cls, bnd, tot
 
 
 @dataclass
 class SuiteResult:
-    """Everything one evaluation produced, still on the device; ``metrics()`` brings it to the host."""
+    """Everything one evaluation produced, still on the device.
+
+    ``class_metrics [N, K, 16]`` / ``boundary_metrics [N, K-1, 3]`` are the float64 scalars (column
+    order ``_lib.CLASS_METRICS`` / ``_lib.BOUNDARY_METRICS``), ``totals`` the dataset-level partial sums
+    of this batch.  ``metrics()`` copies them to the host; ``integers()`` the exact integer outputs."""
     num_items: int
     labels: LabelPassOut
     contours: ContourOut | None
+    class_metrics: torch.Tensor | None = None
+    boundary_metrics: torch.Tensor | None = None
+    totals: torch.Tensor | None = None
+    _inputs: tuple | None = field(default=None, repr=False)
+    _final: bool = field(default=False, repr=False)
     _host: dict | None = field(default=None, repr=False)
+    _totals_host: np.ndarray | None = field(default=None, repr=False)
+
+    def totals_host(self):
+        """The totals vector on the host (one small D2H).  Also where contour overflow is noticed: the
+        vector's last entry ORs all contour flags, and overflowing items are redone before returning."""
+        if self._totals_host is None:
+            vec = self.totals.cpu().numpy()
+            if self.contours is not None and not self._final:
+                self._final = True
+                if int(vec[-1]) & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW):
+                    yt, yp = self._inputs
+                    _retry_overflow(self.contours, yt, yp, self.labels.num_classes, self.labels.first_pos)
+                    self.class_metrics, self.boundary_metrics, self.totals = derive_on_device(
+                        self.labels, self.contours, self.num_items)
+                    vec = self.totals.cpu().numpy()
+            self._inputs = None
+            self._totals_host = vec
+        return self._totals_host
 
     def integers(self):
         """Host copies of the exact integer outputs (numpy; u64/u32 reinterpreted)."""
+        self.totals_host()
         lp, ct = self.labels, self.contours
         d = {}
         if lp.counts is not None:
@@ -256,37 +305,63 @@ class SuiteResult:
         return d
 
     def metrics(self):
-        """float64 ``[N, K]`` (``[N, K-1]`` for boundary errors) arrays keyed by reference function name."""
+        """float64 ``[N, K]`` (``[N, K-1]`` for boundary errors) arrays keyed by reference function name,
+        as computed on the device."""
         if self._host is None:
-            ints = self.integers()
-            m = {}
-            if "confusion" in ints:
-                m.update(derive.count_metrics(*derive.class_counts(ints["confusion"])))
-            if "thickness_absdiff" in ints:
-                m["thickness_difference"] = derive.thickness_difference(ints["thickness_absdiff"], self.labels.width)
-                m.update(derive.boundary_errors(ints["boundary_sq"], ints["boundary_abs"], self.labels.width))
-            if "contour_n_pts" in ints:
-                m.update(derive.contour_metrics(ints["contour_n_pts"], ints["contour_max_sq"],
-                                                ints["contour_p95_sq"], ints["contour_sum_dist"]))
+            self.totals_host()
+            cls = self.class_metrics.cpu().numpy()
+            m = {name: cls[:, :, i] for i, name in enumerate(_lib.CLASS_METRICS)}
+            if self.contours is None:
+                for name in ("hausdorff_distance", "hausdorff_distance_95", "assd"):
+                    m.pop(name)
+            else:
+                m["contour_valid"] = ~np.isnan(m["hausdorff_distance"])
+            if self.labels.thick_absdiff is None:
+                m.pop("thickness_difference")
+            if self.boundary_metrics is not None:
+                b = self.boundary_metrics.cpu().numpy()
+                m.update({name: b[:, :, i] for i, name in enumerate(_lib.BOUNDARY_METRICS)})
             self._host = m
         return self._host
 
+    def metrics_host(self):
+        """The same scalars re-derived on the host from the integer outputs (``derive.py``); the two
+        agree bit for bit (tests/test_gpu_derive.py)."""
+        ints = self.integers()
+        m = {}
+        if "confusion" in ints:
+            m.update(derive.count_metrics(*derive.class_counts(ints["confusion"])))
+        if "thickness_absdiff" in ints:
+            m["thickness_difference"] = derive.thickness_difference(ints["thickness_absdiff"], self.labels.width)
+            m.update(derive.boundary_errors(ints["boundary_sq"], ints["boundary_abs"], self.labels.width))
+        if "contour_n_pts" in ints:
+            m.update(derive.contour_metrics(ints["contour_n_pts"], ints["contour_max_sq"],
+                                            ints["contour_p95_sq"], ints["contour_sum_dist"]))
+        return m
+
 
 def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS, timers=None):
-    """The full suite on a batch of label maps: fused label pass, then the contour kernels.
+    """The full suite on a batch of label maps: fused label pass, contour kernels, float64 epilogue.
 
+    Everything is launched asynchronously on the current stream; nothing is read back until
+    ``totals_host()`` / ``metrics()`` / ``integers()`` is called on the result.
     ``timers``: optional dict filled with (start, end) CUDA-event pairs per kernel family."""
     yt, yp = _check_pair(y_true, y_pred)
     lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries,
                     timers=timers)
-    ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts, timers=timers) if contours else None
-    return SuiteResult(yt.shape[0], lp, ct)
+    ct = None
+    if contours:
+        ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts, timers=timers, check_overflow=False)
+    cls, bnd, tot = derive_on_device(lp, ct, yt.shape[0], timers)
+    return SuiteResult(yt.shape[0], lp, ct, cls, bnd, tot, (yt, yp) if contours else None)
 
 
 def _cat_results(parts):
     def cat(objs, f):
         vals = [getattr(o, f) for o in objs]
         return None if vals[0] is None else torch.cat(vals)
+    for p in parts:
+        p.totals_host()                       # settles any overflow retry per chunk
     lps = [p.labels for p in parts]
     lp = LabelPassOut(lps[0].num_classes, lps[0].height, lps[0].width,
                       *[cat(lps, f) for f in ("counts", "thick_absdiff", "bnd_sq", "bnd_abs", "bnd_true", "bnd_pred",
@@ -296,7 +371,11 @@ def _cat_results(parts):
         cts = [p.contours for p in parts]
         ct = ContourOut(*[cat(cts, f) for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist")], None, None,
                         cts[0].max_pts)
-    return SuiteResult(sum(p.num_items for p in parts), lp, ct)
+    n = sum(p.num_items for p in parts)
+    cls, bnd, tot = derive_on_device(lp, ct, n)            # per-item values again + totals of the whole batch
+    res = SuiteResult(n, lp, ct, cls, bnd, tot)
+    res._final = True
+    return res
 
 
 def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, chunk_items=None,
