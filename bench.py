@@ -142,9 +142,16 @@ def run_b200(args):
 
     timers = {}
 
+    trace = os.environ.get("OCTM_BENCH_TRACE") == "1"
+
     def step():
+        t0 = time.perf_counter()
         res = suite.evaluate(yt, yp, K, contours=not args.no_contours, timers=timers)
+        t1 = time.perf_counter()
         tot = odist.dataset_totals(res, world)          # one small all-reduce (no-op for world == 1)
+        if trace:
+            print(f"[rank {rank}] launch {1e3 * (t1 - t0):.2f} ms, totals+allreduce+D2H {1e3 * (time.perf_counter() - t1):.2f} ms",
+                  file=sys.stderr)
         return res, tot
 
     def barrier():

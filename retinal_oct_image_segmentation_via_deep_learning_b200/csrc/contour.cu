@@ -20,6 +20,7 @@
 //   K7  (same CTA)       max, sum of sqrt(D2/4) in float64, and a radix select of the two order
 //                        statistics numpy's linear 95th percentile interpolates between.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "trace_core.h"
@@ -120,53 +121,58 @@ struct DistParams {
 constexpr int kDistThreads = 128;
 constexpr int kQ = 4;   // queries per thread per sweep
 
+template <int T>
 __device__ __forceinline__ uint32_t block_reduce_max(uint32_t v, uint32_t* scratch) {
     v = __reduce_max_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     uint32_t r = 0;
-    for (int w = 0; w < kDistThreads / 32; ++w) r = max(r, scratch[w]);
+    for (int w = 0; w < T / 32; ++w) r = max(r, scratch[w]);
     __syncthreads();
     return r;
 }
+template <int T>
 __device__ __forceinline__ uint32_t block_reduce_min(uint32_t v, uint32_t* scratch) {
     v = __reduce_min_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     uint32_t r = 0xffffffffu;
-    for (int w = 0; w < kDistThreads / 32; ++w) r = min(r, scratch[w]);
+    for (int w = 0; w < T / 32; ++w) r = min(r, scratch[w]);
     __syncthreads();
     return r;
 }
+template <int T>
 __device__ __forceinline__ uint32_t block_reduce_add(uint32_t v, uint32_t* scratch) {
     v = __reduce_add_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     uint32_t r = 0;
-    for (int w = 0; w < kDistThreads / 32; ++w) r += scratch[w];
+    for (int w = 0; w < T / 32; ++w) r += scratch[w];
     __syncthreads();
     return r;
 }
+template <int T>
 __device__ __forceinline__ double block_reduce_add(double v, double* scratch) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     double r = 0;
-    for (int w = 0; w < kDistThreads / 32; ++w) r += scratch[w];
+    for (int w = 0; w < T / 32; ++w) r += scratch[w];
     __syncthreads();
     return r;
 }
 
 // k-th smallest (0-based) of vals[0..m) by 8-bit radix passes; all threads return the value.
+template <int T>
 __device__ uint32_t block_select(const uint32_t* vals, int m, uint32_t k, uint32_t vmax, uint32_t* hist /*256*/,
                                  uint32_t* bcast /*2*/) {
     uint32_t prefix = 0, maskbits = 0;
     int shift = vmax >= (1u << 24) ? 24 : (vmax >= (1u << 16) ? 16 : (vmax >= (1u << 8) ? 8 : 0));
     for (; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += kDistThreads) hist[i] = 0;
+        for (int i = threadIdx.x; i < 256; i += T) hist[i] = 0;
         __syncthreads();
-        for (int j = threadIdx.x; j < m; j += kDistThreads) {
+        for (int j = threadIdx.x; j < m; j += T) {
             const uint32_t v = vals[j];
             if ((v & maskbits) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
         }
@@ -355,20 +361,20 @@ __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams
                 vmax = max(vmax, v);
                 dsum += sqrt(static_cast<double>(v) / 4.0);
             }
-            vmax = block_reduce_max(vmax, s_scr);
-            dsum = block_reduce_add(dsum, s_dscr);
+            vmax = block_reduce_max<kDistThreads>(vmax, s_scr);
+            dsum = block_reduce_add<kDistThreads>(dsum, s_dscr);
             // numpy linear percentile: virtual index (m - 1) * 0.95, neighbours floor and floor + 1
             const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);
             const uint32_t lo = static_cast<uint32_t>(floor(pos));
-            const uint32_t v_lo = block_select(d2, nq, lo, vmax, s_hist, s_bc);
+            const uint32_t v_lo = block_select<kDistThreads>(d2, nq, lo, vmax, s_hist, s_bc);
             uint32_t cnt_le = 0, next_gt = 0xffffffffu;
             for (int j = threadIdx.x; j < nq; j += kDistThreads) {
                 const uint32_t v = d2[j];
                 cnt_le += v <= v_lo ? 1u : 0u;
                 if (v > v_lo) next_gt = min(next_gt, v);
             }
-            cnt_le = block_reduce_add(cnt_le, s_scr);
-            next_gt = block_reduce_min(next_gt, s_scr);
+            cnt_le = block_reduce_add<kDistThreads>(cnt_le, s_scr);
+            next_gt = block_reduce_min<kDistThreads>(next_gt, s_scr);
             const uint32_t v_hi = (lo + 1 >= static_cast<uint32_t>(nq) || cnt_le >= lo + 2) ? v_lo : next_gt;
             if (prm.sq_out != nullptr) {
                 uint32_t* o = prm.sq_out + (pair * 2 + dir) * static_cast<long long>(cap);
@@ -381,6 +387,153 @@ __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams
                 prm.sum_dist[pair * 2 + dir] = dsum;
             }
             __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ cooperative search
+// Default distance kernel.  A warp owns 32 CONSECUTIVE query vertices (adjacent on their polyline, so
+// they share almost the same neighbourhood of the other contour):
+//   1. box phase, shared by the warp: each lane tests a different source box (16 consecutive source
+//      vertices) against the bounding box of the 32 queries; a ballot yields the candidate boxes;
+//   2. each candidate is re-tested per lane against the lane's own best (one vote decides for the
+//      warp), then scanned by all lanes together: the source vertex is one broadcast LDS.128 and every
+//      lane folds it into its own minimum -- no divergence, 2 IMAD + 1 IMNMX per (query, vertex).
+// The minimum is exact: a box is skipped only when its lower bound cannot beat any lane's best.
+constexpr int kCoopThreads = 256;
+
+__device__ __forceinline__ void coop_scan_box(const int4* src4, int bb, int ns, int cy, int cx, int& bm) {
+    const int i0 = bb * kBox;
+    if (i0 + kBox <= ns) {
+#pragma unroll
+        for (int i = 0; i < kBox; i += 2) {
+            const int4 s0 = src4[i0 + i], s1 = src4[i0 + i + 1];
+            bm = min(bm, min(s0.y * cx + (s0.x * cy + s0.z), s1.y * cx + (s1.x * cy + s1.z)));
+        }
+    } else {
+        for (int i = i0; i < ns; ++i) {
+            const int4 s0 = src4[i];
+            bm = min(bm, s0.y * cx + (s0.x * cy + s0.z));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCoopThreads) distance_coop_kernel(const DistParams prm) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_scr[8];
+    __shared__ double s_dscr[8];
+    __shared__ uint32_t s_bc[2];
+    const int cap = prm.max_pts;
+    int4* const src4 = reinterpret_cast<int4*>(dsm);                                        // {y, x, y^2+x^2, -}
+    uint32_t* const d2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(cap) * 16);
+    int4* const boxes = reinterpret_cast<int4*>(dsm + static_cast<size_t>(cap) * 20);      // {ymin, ymax, xmin, xmax}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
+        const uint32_t n0 = prm.n_pts[pair * 2 + 0], n1 = prm.n_pts[pair * 2 + 1];
+        const int n[2] = {static_cast<int>(min(n0, (uint32_t)cap)), static_cast<int>(min(n1, (uint32_t)cap))};
+        if (n[0] == 0 || n[1] == 0) {
+            if (threadIdx.x < 2) {
+                prm.max_sq[pair * 2 + threadIdx.x] = 0;
+                prm.p95_sq[pair * 4 + threadIdx.x * 2] = prm.p95_sq[pair * 4 + threadIdx.x * 2 + 1] = 0;
+                prm.sum_dist[pair * 2 + threadIdx.x] = 0.0;
+            }
+            continue;
+        }
+        // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
+        for (int dir = 0; dir < 2; ++dir) {
+            const int ns = n[dir], nq = n[1 - dir];
+            const uint32_t* vs = prm.verts + (pair * 2 + dir) * static_cast<long long>(cap);
+            const uint32_t* vq = prm.verts + (pair * 2 + 1 - dir) * static_cast<long long>(cap);
+            __syncthreads();
+            for (int i = threadIdx.x; i < ns; i += kCoopThreads) {
+                const uint32_t v = vs[i];
+                const int y = v >> 16, x = v & 0xffff;
+                src4[i] = make_int4(y, x, y * y + x * x, 0);
+            }
+            __syncthreads();
+            const int nb = (ns + kBox - 1) / kBox;
+            for (int b = threadIdx.x; b < nb; b += kCoopThreads) {
+                int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+                const int e = min(ns, (b + 1) * kBox);
+                for (int i = b * kBox; i < e; ++i) {
+                    const int4 sv = src4[i];
+                    ymin = min(ymin, sv.x); ymax = max(ymax, sv.x); xmin = min(xmin, sv.y); xmax = max(xmax, sv.y);
+                }
+                boxes[b] = make_int4(ymin, ymax, xmin, xmax);
+            }
+            __syncthreads();
+            const float ratio = static_cast<float>(ns) / static_cast<float>(nq);
+            const int nchunks = (nq + 31) >> 5;
+            for (int c = warp; c < nchunks; c += kCoopThreads / 32) {
+                const int j = c * 32 + lane;
+                const uint32_t v = vq[min(j, nq - 1)];          // tail lanes repeat the last query
+                const int qy = v >> 16, qx = v & 0xffff;
+                const int cy = -2 * qy, cx = -2 * qx, qn = qy * qy + qx * qx;
+                const int q_ymin = __reduce_min_sync(0xffffffffu, qy), q_ymax = __reduce_max_sync(0xffffffffu, qy);
+                const int q_xmin = __reduce_min_sync(0xffffffffu, qx), q_xmax = __reduce_max_sync(0xffffffffu, qx);
+                // prime every lane's bound with the box at the same relative position along the other contour
+                const int bg = min(ns - 1, static_cast<int>(static_cast<float>(c * 32 + 16) * ratio)) / kBox;
+                int bm = 0x7fffffff;
+                coop_scan_box(src4, bg, ns, cy, cx, bm);
+                int bestd = bm + qn;
+                int bmax = __reduce_max_sync(0xffffffffu, bestd);
+                for (int b0 = 0; b0 < nb; b0 += 32) {
+                    const int b = b0 + lane;
+                    bool cand = false;
+                    if (b < nb && b != bg) {
+                        const int4 bx = boxes[b];
+                        const int dy = max(max(bx.x - q_ymax, q_ymin - bx.y), 0);
+                        const int dx = max(max(bx.z - q_xmax, q_xmin - bx.w), 0);
+                        cand = dy * dy + dx * dx < bmax;
+                    }
+                    uint32_t mask = __ballot_sync(0xffffffffu, cand);
+                    if (mask == 0) continue;
+                    while (mask) {
+                        const int bb = b0 + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (!__any_sync(0xffffffffu, box_lb2(boxes[bb], qy, qx) < bestd)) continue;
+                        coop_scan_box(src4, bb, ns, cy, cx, bm);
+                        bestd = bm + qn;
+                    }
+                    bmax = __reduce_max_sync(0xffffffffu, bestd);
+                }
+                if (j < nq) d2[j] = static_cast<uint32_t>(bestd);
+            }
+            __syncthreads();
+            // K7: max, sum of sqrt, two order statistics
+            uint32_t vmax = 0;
+            double dsum = 0.0;
+            for (int j = threadIdx.x; j < nq; j += kCoopThreads) {
+                const uint32_t v = d2[j];
+                vmax = max(vmax, v);
+                dsum += sqrt(static_cast<double>(v) / 4.0);
+            }
+            vmax = block_reduce_max<kCoopThreads>(vmax, s_scr);
+            dsum = block_reduce_add<kCoopThreads>(dsum, s_dscr);
+            const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);
+            const uint32_t lo = static_cast<uint32_t>(floor(pos));
+            const uint32_t v_lo = block_select<kCoopThreads>(d2, nq, lo, vmax, s_hist, s_bc);
+            uint32_t cnt_le = 0, next_gt = 0xffffffffu;
+            for (int j = threadIdx.x; j < nq; j += kCoopThreads) {
+                const uint32_t v = d2[j];
+                cnt_le += v <= v_lo ? 1u : 0u;
+                if (v > v_lo) next_gt = min(next_gt, v);
+            }
+            cnt_le = block_reduce_add<kCoopThreads>(cnt_le, s_scr);
+            next_gt = block_reduce_min<kCoopThreads>(next_gt, s_scr);
+            const uint32_t v_hi = (lo + 1 >= static_cast<uint32_t>(nq) || cnt_le >= lo + 2) ? v_lo : next_gt;
+            if (prm.sq_out != nullptr) {
+                uint32_t* o = prm.sq_out + (pair * 2 + dir) * static_cast<long long>(cap);
+                for (int j = threadIdx.x; j < nq; j += kCoopThreads) o[j] = d2[j];
+            }
+            if (threadIdx.x == 0) {
+                prm.max_sq[pair * 2 + dir] = vmax;
+                prm.p95_sq[pair * 4 + dir * 2 + 0] = v_lo;
+                prm.p95_sq[pair * 4 + dir * 2 + 1] = v_hi;
+                prm.sum_dist[pair * 2 + dir] = dsum;
+            }
         }
     }
 }
@@ -440,16 +593,30 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
     const size_t smem = dist_smem(max_pts);
     if (smem > static_cast<size_t>(octm::max_optin_smem()) - 4096)
         return octm::fail(OCTM_ERR_UNSUPPORTED, "max_pts %d needs %zu B of shared memory", max_pts, smem);
-    // OCTM_DISTANCE_BRUTE=1 selects the unpruned kernel (A/B checks; both give identical integers)
-    static const bool brute = [] { const char* e = getenv("OCTM_DISTANCE_BRUTE"); return e && e[0] == '1'; }();
-    auto kern = brute ? octm::distance_kernel<false> : octm::distance_kernel<true>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, octm::max_optin_smem() - 4096) != cudaSuccess)
-        return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
+    // OCTM_DISTANCE_MODE = coop (default) | lane (per-lane pruned search) | brute (no pruning); all three
+    // produce identical integers (tests run the suite under each).
+    static const int mode = [] {
+        const char* e = getenv("OCTM_DISTANCE_MODE");
+        if (e && !strcmp(e, "brute")) return 2;
+        if (e && !strcmp(e, "lane")) return 1;
+        return 0;
+    }();
     octm::DistParams p{verts, n_pts, n_items * num_classes, max_pts, max_sq, p95_sq, sum_dist, sq_out};
     long long grid = n_items * num_classes;
     const long long cap = static_cast<long long>(octm::sm_count()) * 16;
     if (grid > cap) grid = cap;
-    kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == 0) {
+        if (cudaFuncSetAttribute(octm::distance_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 octm::max_optin_smem() - 4096) != cudaSuccess)
+            return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_coop_kernel) failed");
+        octm::distance_coop_kernel<<<static_cast<unsigned>(grid), octm::kCoopThreads, smem, st>>>(p);
+    } else {
+        auto kern = mode == 2 ? octm::distance_kernel<false> : octm::distance_kernel<true>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, octm::max_optin_smem() - 4096) != cudaSuccess)
+            return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
+        kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, st>>>(p);
+    }
     return octm::check_launch("distance_kernel");
 }
 

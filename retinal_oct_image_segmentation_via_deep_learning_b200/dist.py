@@ -99,11 +99,33 @@ def base_len(num_classes):
 def dataset_totals(res, world, device=None, group=None, want_max=False):
     """Dataset-level numbers over all ranks' shards from one SuiteResult per rank.
 
-    The per-rank partial sums come from the device-side totals kernel (one small D2H), are summed
-    across ranks by ONE float64 all-reduce, and unpacked into pooled ratios and per-class means."""
+    The per-rank partial sums come from the device-side totals kernel.  With world > 1 they are
+    summed across ranks by ONE float64 all-reduce issued directly on the device vector (stream
+    ordered after the kernels, no host round trip before the collective); a single small D2H then
+    brings the reduced sums, this rank's maxima and its overflow flags to the host."""
     k, w = res.labels.num_classes, res.labels.width
-    vec = res.totals_host()
     nb = base_len(k)
+    if world > 1 and res.totals is not None and res.totals.is_cuda and not res._final and res._totals_host is None:
+        import torch.distributed as dist
+        local = res.totals
+        reduced = local.clone()
+        dist.all_reduce(reduced[:nb], op=dist.ReduceOp.SUM, group=group)
+        if want_max:
+            dist.all_reduce(reduced[nb:nb + k], op=dist.ReduceOp.MAX, group=group)
+        both = __import__("torch").stack([local, reduced]).cpu().numpy()      # one D2H
+        res._totals_host = None
+        vec_local, vec = both[0], both[1]
+        if int(vec_local[-1]) & 12 and res.contours is not None:             # a contour overflowed on this rank:
+            res.totals_host()                                                 # redo it, then reduce again (rare)
+            return dataset_totals(res, world, device, group, want_max)
+        res._totals_host, res._final, res._inputs = vec_local, True, None
+        if np.any(np.abs(vec_local[:nb - 3 * k]) >= _EXACT_LIMIT):
+            raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")
+        out = unpack(vec[:nb], k, w)
+        if want_max:
+            out["hausdorff_distance_max"] = np.where(vec[nb:nb + k] < 0, np.nan, vec[nb:nb + k])
+        return out
+    vec = res.totals_host()
     base = vec[:nb].copy()
     if np.any(np.abs(base[:nb - 3 * k]) >= _EXACT_LIMIT):
         raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")

@@ -154,11 +154,27 @@ class ContourOut:
     max_pts: int = 0
 
 
+_SCRATCH = {}      # device -> grow-only int32 scratch for contour vertices (pure workspace, never returned)
+
+
+def _vertex_scratch(dev, numel):
+    buf = _SCRATCH.get(dev)
+    if buf is None or buf.numel() < numel:
+        _SCRATCH.pop(dev, None)
+        buf = None
+        buf = torch.empty((numel,), dtype=torch.int32, device=dev)
+        _SCRATCH[dev] = buf
+    return buf[:numel]
+
+
 def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None):
     n, h, w = yt.shape
     dev = yt.device
     i32 = dict(dtype=torch.int32, device=dev)
-    verts = torch.empty((n, k, 2, max_pts), **i32)
+    if want_verts:
+        verts = torch.empty((n, k, 2, max_pts), **i32)
+    else:       # stream-ordered reuse: every consumer of the scratch is enqueued on the same stream
+        verts = _vertex_scratch(dev, n * k * 2 * max_pts).view(n, k, 2, max_pts)
     n_pts = torch.empty((n, k, 2), **i32)
     flags = torch.empty((n, k), **i32)
     max_sq = torch.empty((n, k, 2), **i32)

@@ -1,0 +1,44 @@
+"""GPU parity: the three distance-search strategies (cooperative boxes, per-lane boxes, brute force)
+return identical squared distances -- pruning never changes a result."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import json, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from retinal_oct_image_segmentation_via_deep_learning_b200 import suite, synth
+dev = torch.device("cuda", 0)
+out = {}
+for name, (yt, yp), k in [("layered", synth.layered_pair(3, 200, 256, 6, seed=71, noise=0.002), 6),
+                          ("lesion", synth.lesion_pair(3, 160, 160, 4, seed=72, single_blob_interior=False), 4)]:
+    ct = suite.contour_pass(torch.from_numpy(yt).to(dev), torch.from_numpy(yp).to(dev), k, return_sq=True)
+    n = ct.n_pts.cpu().numpy().view(np.uint32)
+    sq = ct.sq.cpu().numpy().view(np.uint32)
+    tot = 0
+    for i in range(sq.shape[0]):
+        for c in range(k):
+            tot += int(sq[i, c, 0, :n[i, c, 1]].astype(np.int64).sum()) * 7 + int(sq[i, c, 1, :n[i, c, 0]].astype(np.int64).sum())
+    out[name] = [tot, ct.max_sq.cpu().numpy().view(np.uint32).tolist(), ct.p95_sq.cpu().numpy().view(np.uint32).tolist()]
+print(json.dumps(out))
+""" % ROOT
+
+
+def _run(mode):
+    env = dict(os.environ, OCTM_DISTANCE_MODE=mode)
+    r = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_all_modes_agree(cuda):
+    ref = _run("brute")
+    assert _run("coop") == ref
+    assert _run("lane") == ref
