@@ -8,6 +8,6 @@ python bench.py $SMALL > gpurun_out/bench_small.json 2> gpurun_out/bench_small.e
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
     python bench.py $SMALL > gpurun_out/ncu_launches.log 2>&1
 python bench.py $SMALL > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'label_pass_fast|distance_kernel|trace_kernel' -s 3 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:'label_pass_fast|distance_coop_kernel|trace_kernel' -s 4 -c 4 \
     -o gpurun_out/prof_r1 python bench.py $SMALL > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
