@@ -52,6 +52,8 @@ struct LabelPassParams {
     int* bnd_t;
     int* bnd_p;
     unsigned* first_pos;
+    uint32_t one;   // always 1, but opaque to ptxas: `x * one + y` is then an IMAD on the (idle) FMA pipe
+                    // instead of an IADD3 on the ALU pipe that the PRMT-heavy inner loop saturates
 };
 
 // shared-memory carve-up of the fast kernel
@@ -65,17 +67,29 @@ constexpr int kOffWarp = 2048;
 constexpr int kWarpTotals = 2 * 8 * kStrip * 2;    // u16 [map][thr][128]
 constexpr int kWarpHist = 64 * 32 * 2;             // u16 [code][lane]
 constexpr int kWarpQueue = kQueueCap * 16;         // uint4 entries
-constexpr int kWarpBytes = kWarpTotals + kWarpHist + kWarpQueue;
+constexpr int kWarpBytesShort = kWarpHist + kWarpQueue;              // H <= 504: totals alias the histogram block
+constexpr int kWarpBytesTall = kWarpHist + kWarpQueue + kWarpTotals;
+constexpr int kShortRows = 504;   // 18 byte flushes x 7 nibble flushes x 4 rows
 
-__host__ __device__ constexpr uint32_t lut_word(int k1, int k2, int v0) {
+// PRMT look-up words for threshold pair q (k1 = 2q+1, k2 = 2q+2); byte i describes label v0 + i.
+//   q <  2 : flags [v <  k1] | [v <  k2] << 4  -- non-zero only for labels 0-3
+//   q >= 2 : flags [v >= k1] | [v >= k2] << 4  -- non-zero only for labels 4-7
+// The SASS PRMT takes an immediate only as its second data word (labels 4-7), and ptxas re-materialises a
+// register constant before every use, so the "below" pairs are looked up with the selector + 4 per
+// nibble: labels 0-3 then pick the immediate word, labels 4-7 (nibble 8-11) and the pad label (nibble 12)
+// pick a replicated sign bit of a zero byte.  No look-up constant lives in a register.
+// The epilogue turns the "below" counts of thresholds 1-4 back into "at or above" (H - count).
+__host__ __device__ constexpr uint32_t lut_word(int q, int v0) {
+    const int k1 = 2 * q + 1, k2 = 2 * q + 2;
     uint32_t w = 0;
     for (int i = 0; i < 4; ++i) {
         int v = v0 + i;
-        uint32_t b = (v >= k1 ? 1u : 0u) | (v >= k2 ? 0x10u : 0u);
+        uint32_t b = q < 2 ? ((v < k1 ? 1u : 0u) | (v < k2 ? 0x10u : 0u)) : ((v >= k1 ? 1u : 0u) | (v >= k2 ? 0x10u : 0u));
         w |= b << (8 * i);
     }
     return w;
 }
+constexpr int kBelowThresholds = 4;   // thresholds 1..4 are counted as "label below"
 
 // raw PRMT: unlike __byte_perm the selector is not masked to 3 bits per nibble, so nibble value 8
 // (the pad label) selects "sign of byte 0", which is 0x00 for every LUT used here.
@@ -83,6 +97,12 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
 
 // Column-scan state of one lane: 2 word slots x 2 halves; every accumulator byte belongs to one
@@ -140,20 +160,57 @@ struct ColState {
 };
 
 // two rows (A, B) of one word slot: t/p words -> interleaved selector -> LUT flags -> nibble counters
-template <int NP, bool SEEDS>
+template <int NP>
 __device__ __forceinline__ void col_accumulate(uint32_t (&nib)[2][NP], uint32_t tA, uint32_t pA, uint32_t tB,
-                                               uint32_t pB, uint32_t& pres, bool want_pres) {
+                                               uint32_t pB, uint32_t one) {
     const uint32_t xa = pA * 16u + tA, xb = pB * 16u + tB;      // nibbles: t0 p0 t1 p1 | t2 p2 t3 p3
     const uint32_t sel[2][2] = {{xa, xa >> 16}, {xb, xb >> 16}};
+    const uint32_t sel4[2][2] = {{xa * one + 0x44444444u, sel[0][1] * one + 0x4444u},
+                                 {xb * one + 0x44444444u, sel[1][1] * one + 0x4444u}};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            const uint32_t lo = lut_word(2 * q + 1, 2 * q + 2, 0), hi = lut_word(2 * q + 1, 2 * q + 2, 4);
-            nib[h][q] = nib[h][q] + prmt(lo, hi, sel[0][h]) + prmt(lo, hi, sel[1][h]);
+            const uint32_t fa = q < 2 ? prmt(0u, lut_word(q, 0), sel4[0][h]) : prmt(0u, lut_word(q, 4), sel[0][h]);
+            const uint32_t fb = q < 2 ? prmt(0u, lut_word(q, 0), sel4[1][h]) : prmt(0u, lut_word(q, 4), sel[1][h]);
+            nib[h][q] = fb * one + (fa * one + nib[h][q]);
         }
-        if (SEEDS && want_pres)
-            pres |= prmt(0x08040201u, 0x80402010u, sel[0][h]) | prmt(0x08040201u, 0x80402010u, sel[1][h]);
+    }
+}
+
+// classes present among one lane's 16 pixel pairs: bits 0-7 y_true, bits 8-15 y_pred (pad label 8 -> none)
+__device__ __forceinline__ uint32_t presence_bits(uint2 tA, uint2 pA, uint2 tB, uint2 pB) {
+    const uint32_t x0 = pA.x * 16u + tA.x, x1 = pA.y * 16u + tA.y, x2 = pB.x * 16u + tB.x, x3 = pB.y * 16u + tB.y;
+    const uint32_t lo = 0x08040201u, hi = 0x80402010u;
+    const uint32_t w = (prmt(lo, hi, x0) | prmt(lo, hi, x0 >> 16)) | (prmt(lo, hi, x1) | prmt(lo, hi, x1 >> 16)) |
+                       (prmt(lo, hi, x2) | prmt(lo, hi, x2 >> 16)) | (prmt(lo, hi, x3) | prmt(lo, hi, x3 >> 16));
+    return (w | (w >> 16)) & 0xffffu;
+}
+
+// index (0-7) of the first byte equal to c in the 8 labels {w.x, w.y}, or 8
+__device__ __forceinline__ uint32_t first_match8(uint2 w, uint32_t cc) {
+    const uint32_t z0 = ~((w.x ^ cc) + 0x7f7f7f7fu) & 0x80808080u;   // labels < 16: exact zero-byte test
+    const uint32_t z1 = ~((w.y ^ cc) + 0x7f7f7f7fu) & 0x80808080u;
+    if (z0) return (__ffs(z0) - 1) >> 3;
+    if (z1) return 4 + ((__ffs(z1) - 1) >> 3);
+    return 8;
+}
+
+// a lane met classes `fresh` (bits as presence_bits) for the first time in this item: fold the raster
+// position of their first pixel among its rows A (at posA) and B (at posB) into the CTA's table
+__device__ __forceinline__ void record_first(uint32_t fresh, uint2 tA, uint2 pA, uint2 tB, uint2 pB, uint32_t posA,
+                                             uint32_t posB, uint32_t* cta_first) {
+    while (fresh) {
+        const int bit = __ffs(fresh) - 1;
+        fresh &= fresh - 1;
+        const int m = bit >> 3, c = bit & 7;
+        const uint32_t cc = 0x01010101u * c;
+        uint32_t i = first_match8(m ? pA : tA, cc), pos = posA + i;
+        if (i == 8) {
+            i = first_match8(m ? pB : tB, cc);
+            pos = posB + i;
+        }
+        if (i < 8 && pos < cta_first[m * 16 + c]) atomicMin(&cta_first[m * 16 + c], pos);
     }
 }
 
@@ -190,11 +247,108 @@ __device__ __forceinline__ void conf_push(bool mixed_lane, uint4 e, unsigned sho
     }
 }
 
+// per-lane running state of one item
+template <int NP>
+struct LaneState {
+    ColState<NP> cs;
+    uint32_t qhead, qtail;
+    uint32_t last_b;      // joint code (byte-replicated) of this lane's last uniform row pair
+    uint32_t warp_seen;   // classes this warp has met in this item (presence_bits layout, warp-uniform)
+    int nib_fill, byt_fill;
+    __device__ __forceinline__ void reset(bool cols) {
+        if (cols) cs.clear();
+        qhead = qtail = 0;
+        last_b = 0xffffffffu;
+        warp_seen = 0;
+        nib_fill = byt_fill = 0;
+    }
+};
+
+struct StageConsts {
+    uint32_t W2, W4, map_bytes, one;
+    int phase, lane;
+    bool colv;
+    unsigned short* hist_lane;
+    uint4* queue;
+    unsigned short* totals;
+    uint32_t* cta_first;
+};
+
+// One ring stage (rows x strip) of one consumer warp.  Each pass of the loop takes 4 rows: lanes 0-15 rows
+// (4i, 4i+2), lanes 16-31 rows (4i+1, 4i+3), 8 columns per lane, both maps.  FULL: every lane has both rows
+// (no predicates); otherwise missing rows / columns are replaced by the pad label.
+// Kept rolled: one pass is ~100 instructions and must stay inside the L0 instruction cache.
+template <int NP, bool CONF, bool COLS, bool SEEDS, bool FULL>
+__device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint32_t pos, int rows, const StageConsts& sc) {
+    const int npairs = (rows + 3) >> 2;
+#pragma unroll 1
+    for (int pr = 0; pr < npairs; ++pr, at += sc.W4, pos += sc.W4) {
+        uint2 tA, pA, tB, pB;
+        bool va = true, vb = true;
+        if (FULL) {
+            tA = lds64(at);
+            tB = lds64(at + sc.W2);
+            pA = lds64(at + sc.map_bytes);
+            pB = lds64(at + sc.map_bytes + sc.W2);
+        } else {
+            va = sc.colv && 4 * pr + sc.phase < rows;
+            vb = sc.colv && 4 * pr + sc.phase + 2 < rows;
+            tA = make_uint2(kPadWord, kPadWord); pA = tA; tB = tA; pB = tA;
+            if (va) { tA = lds64(at); pA = lds64(at + sc.map_bytes); }
+            if (vb) { tB = lds64(at + sc.W2); pB = lds64(at + sc.map_bytes + sc.W2); }
+        }
+        if (COLS) {
+            col_accumulate<NP>(ls.cs.nib[0], tA.x, pA.x, tB.x, pB.x, sc.one);
+            col_accumulate<NP>(ls.cs.nib[1], tA.y, pA.y, tB.y, pB.y, sc.one);
+        }
+        if (CONF || SEEDS) {
+            uint4 j = make_uint4(tA.x * 8u + pA.x, tA.y * 8u + pA.y, tB.x * 8u + pB.x, tB.y * 8u + pB.y);
+            const uint32_t b = prmt(j.x, 0, 0);
+            // uniform lane: all 16 pixel pairs share one joint code (padded lanes never take this path)
+            const bool uni = FULL && (((j.x ^ b) | (j.y ^ b)) | ((j.z ^ b) | (j.w ^ b))) == 0;
+            if (CONF && uni) hist_add(sc.hist_lane, b & 0x3fu, 16);
+            const bool changed = SEEDS && uni && b != ls.last_b;
+            if (SEEDS && uni) ls.last_b = b;
+            const bool mixed_lane = FULL ? !uni : (va || vb);
+            if (__any_sync(0xffffffffu, mixed_lane || changed)) {
+                if (SEEDS) {
+                    // classes are tracked per WARP: rows only grow from pass to pass, so once any lane has
+                    // met a class, later passes cannot hold an earlier pixel of it
+                    uint32_t fresh = 0;
+                    if (changed || mixed_lane) {
+                        const uint32_t bits = uni ? ((1u << ((b >> 3) & 7u)) | (0x100u << (b & 7u)))
+                                                  : presence_bits(tA, pA, tB, pB);
+                        fresh = bits & ~ls.warp_seen;
+                    }
+                    const uint32_t any_fresh = __reduce_or_sync(0xffffffffu, fresh);
+                    if (any_fresh) {
+                        ls.warp_seen |= any_fresh;
+                        if (fresh) record_first(fresh, tA, pA, tB, pB, pos, pos + sc.W2, sc.cta_first);
+                    }
+                }
+                __syncwarp();
+                if (CONF) {
+                    if (!FULL) {
+                        if (!va) j.x = j.y = kSkipWord;
+                        if (!vb) j.z = j.w = kSkipWord;
+                    }
+                    conf_push(mixed_lane, j, sc.hist_lane, sc.queue, ls.qhead, ls.qtail, sc.lane);
+                }
+            }
+        }
+        if (COLS && ++ls.nib_fill == 7) {
+            ls.cs.nib_to_byte();
+            ls.nib_fill = 0;
+            if (++ls.byt_fill == 18) { ls.byt_fill = 0; ls.cs.byte_to_totals(sc.totals, sc.lane); }
+        }
+    }
+}
+
 template <int NP, bool CONF, bool COLS, bool SEEDS, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_pass_fast(const LabelPassParams prm) {
+__global__ void __launch_bounds__(WIDE ? 16 * 32 : 8 * 32, WIDE ? 1 : 2) label_pass_fast(const LabelPassParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int NW = (blockDim.x >> 5) - 1;
+    const int NW = blockDim.x >> 5;
     const int H = prm.H, W = prm.W, K = prm.K, R = prm.R, S = prm.S;
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -204,172 +358,127 @@ __global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_p
     unsigned long long* cta_abs = reinterpret_cast<unsigned long long*>(smem + kOffAbs);
     unsigned long long* cta_thick = reinterpret_cast<unsigned long long*>(smem + kOffThick);
     uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + kOffFirst);
-    uint8_t* ring = smem + ((kOffWarp + NW * kWarpBytes + 127) & ~127);
+    const bool tall = H > kShortRows;
+    const int warp_bytes = tall ? kWarpBytesTall : kWarpBytesShort;
+    uint8_t* ring = smem + ((kOffWarp + NW * warp_bytes + 127) & ~127);
     const uint32_t map_bytes = static_cast<uint32_t>(R) * W;
     const uint32_t stage_bytes = 2 * map_bytes;
 
     for (int i = tid; i < 256; i += blockDim.x) cta_counts[i] = 0;
     if (tid < 16) cta_sq[tid] = cta_abs[tid] = cta_thick[tid] = 0;
     if (tid < 32) cta_first[tid] = OCTM_NO_SEED;
-    for (int i = tid; i < NW * kWarpBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + kOffWarp)[i] = 0;
+    for (int i = tid; i < NW * warp_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + kOffWarp)[i] = 0;
+    uint32_t* done_cnt = reinterpret_cast<uint32_t*>(empty);   // warps finished with the slot's current fill
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NW);
+            done_cnt[s] = 0;
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == NW) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
-            uint32_t s = 0, ph = 0;
-            for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-                const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
-                const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
-                for (int r0 = 0; r0 < H; r0 += R) {
-                    const int rows = min(R, H - r0);
-                    mbar_wait_parked(&empty[s], ph ^ 1);
-                    const uint32_t bytes = static_cast<uint32_t>(rows) * W;
-                    mbar_arrive_expect_tx(&full[s], 2 * bytes);
-                    uint8_t* dst = ring + static_cast<size_t>(s) * stage_bytes;
-                    bulk_g2s(dst, bt + static_cast<long long>(r0) * W, bytes, &full[s], pol);
-                    bulk_g2s(dst + map_bytes, bp + static_cast<long long>(r0) * W, bytes, &full[s], pol);
-                    if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-        return;
+    // ---------------------------------------------------------------------- ring fills
+    // There is no producer warp.  The CTA's stages form one fixed sequence (item by item, R rows at a
+    // time); fill f lives in slot f % S.  The LAST warp to finish a slot (shared-memory counter) issues
+    // fill f + S into it: two 1-D TMA bulk copies (one per map) completing on the slot's mbarrier.
+    // Every warp tracks the coordinates of fill f + S in registers (nf_item, nf_r0).
+    const uint64_t pol = policy_evict_first();
+    auto issue_fill = [&](long long it, int r0, uint32_t slot) {
+        const uint32_t bytes = static_cast<uint32_t>(min(R, H - r0)) * W;
+        const long long off = (it * H + r0) * static_cast<long long>(W);
+        uint8_t* dst = ring + static_cast<size_t>(slot) * stage_bytes;
+        mbar_arrive_expect_tx(&full[slot], 2 * bytes);
+        bulk_g2s(dst, prm.yt + off, bytes, &full[slot], pol);
+        bulk_g2s(dst + map_bytes, prm.yp + off, bytes, &full[slot], pol);
+    };
+    long long nf_item = blockIdx.x;
+    int nf_r0 = 0;
+    for (int f = 0; f < S; ++f) {
+        if (tid == 0 && nf_item < prm.n_items) issue_fill(nf_item, nf_r0, f);
+        nf_r0 += R;
+        if (nf_r0 >= H) { nf_r0 = 0; nf_item += gridDim.x; }
     }
 
     // ---------------------------------------------------------------------- consumers
-    uint8_t* wbase = smem + kOffWarp + warp * kWarpBytes;
-    unsigned short* totals = reinterpret_cast<unsigned short*>(wbase);                       // [2][8][128]
-    unsigned short* hist = reinterpret_cast<unsigned short*>(wbase + kWarpTotals);           // [64][32]
+    uint8_t* wbase = smem + kOffWarp + warp * warp_bytes;
+    unsigned short* hist = reinterpret_cast<unsigned short*>(wbase);                         // [64][32]
     unsigned short* hist_lane = hist + lane;
-    uint4* queue = reinterpret_cast<uint4*>(wbase + kWarpTotals + kWarpHist);
+    uint4* queue = reinterpret_cast<uint4*>(wbase + kWarpHist);
+    unsigned short* totals = tall ? reinterpret_cast<unsigned short*>(wbase + kWarpHist + kWarpQueue) : hist;   // [2][8][128]
     const int phase = lane >> 4;
     const int col = warp * kStrip + (lane & 15) * 8;      // first of this lane's 8 columns
     const bool colv = col < W;
     const bool strip_full = (warp + 1) * kStrip <= W;      // warp-uniform
     const int nthr = K - 1;
     const int consumers = NW * 32;
-    const uint32_t all_found = ((1u << K) - 1u) * 0x101u;
     const uint32_t lane_off = static_cast<uint32_t>(phase) * W + col;
+    const uint32_t ring_addr = smem_u32(ring);
 
-    ColState<NP> cs;
+    StageConsts sc;
+    sc.W2 = 2u * W; sc.W4 = 4u * W; sc.map_bytes = map_bytes; sc.one = prm.one;
+    sc.phase = phase; sc.lane = lane; sc.colv = colv;
+    sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.cta_first = cta_first;
+    LaneState<NP> ls;
     uint32_t s = 0, ph = 0;
     for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-        if (COLS) cs.clear();
-        uint32_t qhead = 0, qtail = 0;
-        uint32_t found = 0;
-        int nib_fill = 0, byt_fill = 0;
+        ls.reset(COLS);
 
         for (int r0 = 0; r0 < H; r0 += R) {
             const int rows = min(R, H - r0);
             mbar_wait(&full[s], ph);
-            const uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes + lane_off;   // this lane's first row
-            const uint8_t* sp = st + map_bytes;
-            uint32_t pres = 0;
-            const bool want_pres = SEEDS && found != all_found;
-            const int npairs = (rows + 3) >> 2;
-            if (strip_full && (rows & 3) == 0) {
-                // -------- every lane has both of its rows: no predicates.  Not unrolled: one pass is
-                // ~140 instructions and must stay inside the 6 KB L0 instruction cache.
-#pragma unroll 1
-                for (int pr = 0; pr < npairs; ++pr) {
-                    const uint2 tA = *reinterpret_cast<const uint2*>(st + (4 * pr) * W);
-                    const uint2 pA = *reinterpret_cast<const uint2*>(sp + (4 * pr) * W);
-                    const uint2 tB = *reinterpret_cast<const uint2*>(st + (4 * pr + 2) * W);
-                    const uint2 pB = *reinterpret_cast<const uint2*>(sp + (4 * pr + 2) * W);
-                    if (COLS || SEEDS) {
-                        col_accumulate<NP, SEEDS>(cs.nib[0], tA.x, pA.x, tB.x, pB.x, pres, want_pres);
-                        col_accumulate<NP, SEEDS>(cs.nib[1], tA.y, pA.y, tB.y, pB.y, pres, want_pres);
-                    }
-                    if (CONF) {
-                        const uint4 j = make_uint4(tA.x * 8u + pA.x, tA.y * 8u + pA.y, tB.x * 8u + pB.x, tB.y * 8u + pB.y);
-                        const uint32_t b = prmt(j.x, 0, 0);
-                        const bool uni = (((j.x ^ b) | (j.y ^ b)) | ((j.z ^ b) | (j.w ^ b))) == 0;
-                        if (uni) hist_add(hist_lane, b & 0x3fu, 16);
-                        conf_push(!uni, j, hist_lane, queue, qhead, qtail, lane);
-                    }
-                    if (COLS && ++nib_fill == 7) {
-                        cs.nib_to_byte();
-                        nib_fill = 0;
-                        if (++byt_fill == 18) { byt_fill = 0; cs.byte_to_totals(totals, lane); }
-                    }
-                }
-            } else {
-                // -------- ragged strip or last rows of the item: per-row validity
-                for (int pr = 0; pr < npairs; ++pr) {
-                    const int ra = 4 * pr + phase, rb = ra + 2;
-                    const bool va = colv && ra < rows, vb = colv && rb < rows;
-                    uint2 tA = make_uint2(kPadWord, kPadWord), pA = tA, tB = tA, pB = tA;
-                    if (va) {
-                        tA = *reinterpret_cast<const uint2*>(st + (4 * pr) * W);
-                        pA = *reinterpret_cast<const uint2*>(sp + (4 * pr) * W);
-                    }
-                    if (vb) {
-                        tB = *reinterpret_cast<const uint2*>(st + (4 * pr + 2) * W);
-                        pB = *reinterpret_cast<const uint2*>(sp + (4 * pr + 2) * W);
-                    }
-                    if (COLS || SEEDS) {
-                        col_accumulate<NP, SEEDS>(cs.nib[0], tA.x, pA.x, tB.x, pB.x, pres, want_pres);
-                        col_accumulate<NP, SEEDS>(cs.nib[1], tA.y, pA.y, tB.y, pB.y, pres, want_pres);
-                    }
-                    if (CONF) {
-                        uint4 j = make_uint4(tA.x * 8u + pA.x, tA.y * 8u + pA.y, tB.x * 8u + pB.x, tB.y * 8u + pB.y);
-                        if (!va) j.x = j.y = kSkipWord;
-                        if (!vb) j.z = j.w = kSkipWord;
-                        conf_push(va || vb, j, hist_lane, queue, qhead, qtail, lane);
-                    }
-                    if (COLS && ++nib_fill == 7) {
-                        cs.nib_to_byte();
-                        nib_fill = 0;
-                        if (++byt_fill == 18) { byt_fill = 0; cs.byte_to_totals(totals, lane); }
-                    }
-                }
-            }
-            if (SEEDS && want_pres) {
-                // classes seen in this stage: bits 0-7 y_true, 8-15 y_pred
-                uint32_t fresh = __reduce_or_sync(0xffffffffu, ((pres | (pres >> 16)) & 0xffffu) & ~found);
-                found |= fresh;
-                const uint8_t* st0 = st - lane_off + col;      // row 0 of the stage, this lane's columns
-                while (fresh) {
-                    const int bit = __ffs(fresh) - 1;
-                    fresh &= fresh - 1;
-                    const int m = bit >> 3, c = bit & 7;
-                    const uint8_t* sm = m ? st0 + map_bytes : st0;
-                    const uint32_t cc = 0x01010101u * c;
-                    for (int pp = 0; pp < (rows + 1) / 2; ++pp) {
-                        const int rr = 2 * pp + phase;
-                        uint32_t cand = OCTM_NO_SEED;
-                        if (colv && rr < rows) {
-                            const uint2 w = *reinterpret_cast<const uint2*>(sm + rr * W);
-                            const uint32_t z0 = ~((w.x ^ cc) + 0x7f7f7f7fu) & 0x80808080u;
-                            const uint32_t z1 = ~((w.y ^ cc) + 0x7f7f7f7fu) & 0x80808080u;
-                            if (z0) cand = (r0 + rr) * W + col + ((__ffs(z0) - 1) >> 3);
-                            else if (z1) cand = (r0 + rr) * W + col + 4 + ((__ffs(z1) - 1) >> 3);
-                        }
-                        const uint32_t best = __reduce_min_sync(0xffffffffu, cand);
-                        if (best != OCTM_NO_SEED) {
-                            if (lane == 0) atomicMin(&cta_first[m * 16 + c], best);
-                            break;
-                        }
-                    }
-                }
-            }
+            const uint32_t at = ring_addr + s * stage_bytes + lane_off;      // this lane's first row, y_true
+            const uint32_t pos = static_cast<uint32_t>(r0) * W + lane_off;    // its raster index in the item
+            if (strip_full && (rows & 3) == 0)       // warp-uniform: every lane has both of its rows
+                stage_rows<NP, CONF, COLS, SEEDS, true>(ls, at, pos, rows, sc);
+            else                                     // ragged strip or last rows of the item
+                stage_rows<NP, CONF, COLS, SEEDS, false>(ls, at, pos, rows, sc);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done_cnt[s], 1u) == static_cast<uint32_t>(NW - 1)) {
+                    // every warp is done with this slot: refill it (fence orders their reads before the copy)
+                    done_cnt[s] = 0;
+                    __threadfence_block();
+                    fence_proxy_async();
+                    if (nf_item < prm.n_items) issue_fill(nf_item, nf_r0, s);
+                }
+            }
+            nf_r0 += R;
+            if (nf_r0 >= H) { nf_r0 = 0; nf_item += gridDim.x; }
             if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
         }
 
         // ------------------------------------------------------------------ item epilogue
+        // The histogram fold runs first and leaves its shared-memory block zeroed: for items of at most
+        // 504 rows (no mid-item byte flush) the column totals reuse that block.
+        if (CONF) {
+            // leftover queue entries, then fold the 32 private histogram columns
+            const uint32_t left = ls.qtail - ls.qhead;
+            __syncwarp();
+            if (static_cast<uint32_t>(lane) < left) drain_entry(hist_lane, queue[(ls.qhead + lane) & (kQueueCap - 1)]);
+            __syncwarp();
+            uint32_t* h32 = reinterpret_cast<uint32_t*>(hist);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int code = lane * 2 + cc;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = (lane + i) & 15;
+                    const uint32_t w = h32[code * 16 + j];
+                    h32[code * 16 + j] = 0;
+                    lo += w & 0xffffu;
+                    hi += w >> 16;
+                }
+                if (lo + hi) atomicAdd(&cta_counts[code], lo + hi);
+            }
+        }
+
+        __syncwarp();
         if (COLS) {
-            cs.nib_to_byte();
-            cs.byte_to_totals(totals, lane);
+            ls.cs.nib_to_byte();
+            ls.cs.byte_to_totals(totals, lane);
             // per-column arithmetic: lane owns 4 columns of the strip
             const int lc = lane * 4;
             const bool cv = warp * kStrip + lc < W;
@@ -389,8 +498,12 @@ __global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_p
                     const uint2 a = *pt, b = *pp;
                     *pt = make_uint2(0, 0);
                     *pp = make_uint2(0, 0);
-                    const int cut[4] = {int(a.x & 0xffff), int(a.x >> 16), int(a.y & 0xffff), int(a.y >> 16)};
-                    const int cup[4] = {int(b.x & 0xffff), int(b.x >> 16), int(b.y & 0xffff), int(b.y >> 16)};
+                    int cut[4] = {int(a.x & 0xffff), int(a.x >> 16), int(a.y & 0xffff), int(a.y >> 16)};
+                    int cup[4] = {int(b.x & 0xffff), int(b.x >> 16), int(b.y & 0xffff), int(b.y >> 16)};
+                    if (j < kBelowThresholds) {      // thresholds 1-4 were counted as "label below"
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { cut[i] = H - cut[i]; cup[i] = H - cup[i]; }
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int d = cut[i] - cup[i];
@@ -429,29 +542,6 @@ __global__ void __launch_bounds__(WIDE ? 17 * 32 : 9 * 32, WIDE ? 1 : 2) label_p
                 }
             }
         }
-        if (CONF) {
-            // leftover queue entries, then fold the 32 private histogram columns
-            const uint32_t left = qtail - qhead;
-            __syncwarp();
-            if (static_cast<uint32_t>(lane) < left) drain_entry(hist_lane, queue[(qhead + lane) & (kQueueCap - 1)]);
-            __syncwarp();
-            uint32_t* h32 = reinterpret_cast<uint32_t*>(hist);
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int code = lane * 2 + cc;
-                uint32_t lo = 0, hi = 0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = (lane + i) & 15;
-                    const uint32_t w = h32[code * 16 + j];
-                    h32[code * 16 + j] = 0;
-                    lo += w & 0xffffu;
-                    hi += w >> 16;
-                }
-                if (lo + hi) atomicAdd(&cta_counts[code], lo + hi);
-            }
-        }
-
         named_bar_sync(1, consumers);
         {
             const int ct_id = warp * 32 + lane;
@@ -605,19 +695,21 @@ static bool fast_ok(int H, int W, int K, const void* a, const void* b) {
 template <int NP, bool CONF, bool COLS, bool SEEDS>
 static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     LabelPassParams p = p0;
+    p.one = 1;
     const int NW = (p.W + kStrip - 1) / kStrip;
-    // rows per stage: ~6 KB per map (multiple of 4 rows), 3 stages in flight per CTA.
+    // rows per stage: ~8 KB per map (multiple of 4 rows), 2 stages per CTA: with 4 resident CTAs per SM that
+    // is 8 fills in flight per SM, and occupancy (shared memory) matters more than ring depth here.
     // OCTM_LP_ROWS / OCTM_LP_STAGES override for tuning runs.
     static const int env_rows = [] { const char* e = getenv("OCTM_LP_ROWS"); return e ? atoi(e) : 0; }();
     static const int env_stages = [] { const char* e = getenv("OCTM_LP_STAGES"); return e ? atoi(e) : 0; }();
-    int R = (6144 / p.W) & ~3;
+    int R = (8192 / p.W) & ~3;
     if (env_rows > 0) R = env_rows & ~3;
     if (R < 4) R = 4;
     p.R = R;
-    const int fixed = ((kOffWarp + NW * kWarpBytes + 127) & ~127);
+    const int fixed = ((kOffWarp + NW * (p.H > kShortRows ? kWarpBytesTall : kWarpBytesShort) + 127) & ~127);
     const int stage = 2 * R * p.W;
     const int budget = max_optin_smem();
-    int S = env_stages >= 2 && env_stages <= kMaxStages ? env_stages : 3;
+    int S = env_stages >= 2 && env_stages <= kMaxStages ? env_stages : 2;
     while (S > 2 && fixed + S * stage > budget) --S;
     p.S = S;
     const int smem = fixed + S * stage;
@@ -625,10 +717,12 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     auto kern = NW > 8 ? label_pass_fast<NP, CONF, COLS, SEEDS, true> : label_pass_fast<NP, CONF, COLS, SEEDS, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess)
         return fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(label_pass_fast) failed");
-    int per_sm = budget / smem;
-    const int threads = (NW + 1) * 32;
-    if (per_sm * threads > 2048) per_sm = 2048 / threads;
-    if (per_sm < 1) per_sm = 1;
+    const int threads = NW * 32;
+    int per_sm = 0;      // persistent grid: exactly the CTAs that are resident at once
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
     long long grid = static_cast<long long>(sm_count()) * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p);
