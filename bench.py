@@ -15,6 +15,7 @@ per-function Python loops, all host cores) on a bounded sample of the same workl
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -49,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -57,17 +58,23 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken inside [t0, t1] (perf_counter; all samples if none fall inside).
+        The process is started BEFORE the warm-up: nvidia-smi's own start-up (NVML init) stalls CUDA calls
+        for tens of milliseconds on a fresh box and must not land in the timed region."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if t0 is None or t0 <= t <= t1 + 0.15]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -160,14 +167,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)                      # let nvidia-smi finish initialising before anything is timed
     for _ in range(args.warmup):
         step()
     barrier()
     timers.clear()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    gc.collect()
+    gc.disable()          # a generational collection inside a ~15 ms step is a 10 ms host stall
     launches0 = _lib.launch_count()
+    t_begin = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -175,8 +186,9 @@ def run_b200(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    gc.enable()
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.perf_counter()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -218,6 +230,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int(m * BYTES_PER_BSCAN), "d2h_bytes_per_step": int(d2h),
                "items_per_step_per_gpu": m, "steps": e2e_steps}
 
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None   # device-timed + e2e regions
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -245,7 +258,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--items", type=int, default=16384, help="B-scans per GPU per step")

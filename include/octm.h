@@ -138,8 +138,9 @@ OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int
 /* The two stages of the above, exposed for tests and for callers that want the vertices.
  *   verts   uint32 [n][K][2][max_pts]  packed (y2 << 16 | x2) doubled-lattice vertices in trace
  *                                      order (the closing repeat, if any, is the last entry)
- *   sq_out  uint32 [n][K][2][max_pts]  optional per-query-vertex D2 (direction d stores the D2 of
- *                                      the vertices of map 1-d... see DESIGN.md), may be NULL */
+ *   d2      uint32 [n][K][2][max_pts]  per-query-vertex D2: [i][c][d][j] = squared distance from vertex j
+ *                                      of map 1-d to the nearest vertex of map d.  Required: it is also
+ *                                      the scratch between the search and the select kernel. */
 OCTM_API int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t item_elems, int num_classes,
                       uint32_t* first_pos /* [n][K] */, void* stream);
 OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H,
@@ -147,7 +148,7 @@ OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pre
                             uint32_t* verts, uint32_t* n_pts, uint32_t* flags, void* stream);
 OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items,
                             int num_classes, int max_pts, uint32_t* max_sq, uint32_t* p95_sq,
-                            double* sum_dist, uint32_t* sq_out, void* stream);
+                            double* sum_dist, uint32_t* d2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Float64 epilogue on the device.  class_metrics[i][c][m] (double [n][K][OCTM_NUM_CLASS_METRICS]) holds

@@ -14,11 +14,14 @@
 //   K5  trace_kernel     one thread per (item, class, map): locate the raster-first mixed square
 //                        from the label pass's first-occurrence table, walk the polyline forward
 //                        (and backward if it is open), emit doubled-lattice vertices.
-//   K6  distance_kernel  one CTA per (item, class): both vertex lists in shared memory; exact
-//                        integer squared distances with the expansion |a|^2 - 2 a.q + |q|^2 so the
-//                        inner loop is 2 IMAD + 1 IMNMX per pair, 4 queries per thread.
-//   K7  (same CTA)       max, sum of sqrt(D2/4) in float64, and a radix select of the two order
-//                        statistics numpy's linear 95th percentile interpolates between.
+//   K6  distance_search_kernel  one CTA per (item, class, direction): source contour staged in shared
+//                        memory tile by tile; exact integer squared distances with the expansion
+//                        |a|^2 - 2 a.q + |q|^2 (2 IMAD + 1 IMNMX per pair), pruned by bounding boxes.
+//   K7  distance_select_kernel  one warp per (item, class, direction): max, sum of sqrt(D2/4) in
+//                        float64, and a radix select of the two order statistics numpy's linear 95th
+//                        percentile interpolates between.
+//       distance_kernel  single-kernel brute-force / per-lane-pruned variants (OCTM_DISTANCE_MODE),
+//                        kept as independent checks of the default path.
 #include <cstdlib>
 #include <cstring>
 
@@ -39,13 +42,24 @@ struct TraceParams {
 };
 
 __global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
-    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_step[64];      // step_word table: (case, entry edge) -> exit edge, vertex offset, order
+    if (threadIdx.x < 64) s_step[threadIdx.x] = step_word(threadIdx.x);
+    __syncthreads();
     const int K = prm.K, H = prm.H, W = prm.W;
-    if (gid >= prm.n_items * K * 2) return;
-    // consecutive threads: same item, same map, consecutive classes (they walk nearby pixels)
-    const long long item = gid / (2 * K);
-    const int m = static_cast<int>((gid / K) % 2);
-    const int cls = static_cast<int>(gid % K);
+    const long long total = prm.n_items * K * 2;
+    // persistent CTAs (grid = SMs x a tuned number of CTAs per SM): the walks of the resident warps must
+    // keep their few label rows in L1, so occupancy is capped by the launch, not by registers
+    for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < total;
+         base += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long gid = base + threadIdx.x;
+    if (gid >= total) continue;
+    // warps are homogeneous in the map (contours of y_true and of y_pred differ in length, and a warp
+    // runs as long as its longest walk): consecutive threads = same map, consecutive (item, class)
+    const long long per_map = prm.n_items * K;
+    const int m = gid >= per_map ? 1 : 0;
+    const long long rem = gid - m * per_map;
+    const long long item = rem / K;
+    const int cls = static_cast<int>(rem % K);
     const uint8_t* L = (m ? prm.yp : prm.yt) + item * H * static_cast<long long>(W);
     uint32_t* out = prm.verts + ((item * K + cls) * 2 + m) * static_cast<long long>(prm.max_pts);
     const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
@@ -65,11 +79,40 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
     }
     if (seed != OCTM_NO_SEED) {
         const uint32_t cap = static_cast<uint32_t>(prm.max_pts);
+        uint32_t g0 = 0, g1 = 0, g2 = 0;
+        const uint32_t c4 = 0x01010101u * static_cast<uint32_t>(cls);
         const TraceResult r = trace_first_contour(
             H, W, seed,
+            [&](int r0, int c0) -> int {
+                const uint8_t* p = L + (static_cast<uint32_t>(r0) * static_cast<uint32_t>(W) + static_cast<uint32_t>(c0));
+                // four labels -> one word -> exact zero-byte test against the class (labels < 16)
+                const uint32_t w = __ldg(p) | (__ldg(p + 1) << 8) | (__ldg(p + W) << 16) | (__ldg(p + W + 1) << 24);
+                const uint32_t z = ~((w ^ c4) + 0x7f7f7f7fu) & 0x80808080u;
+                return static_cast<int>(((z >> 7) * 0x01020408u) >> 24);
+            },
+            [&](int r0, int c0, int e) -> int {
+                // the two pixels not shared with the previous square (trace_core.h: carried_bits)
+                const uint8_t* p = L + (static_cast<uint32_t>(r0) * static_cast<uint32_t>(W) + static_cast<uint32_t>(c0));
+                const int oa = (e == 1 ? W : 0) + (e == 3 ? 1 : 0), ob = oa + ((e & 2) ? W : 1);
+                return (__ldg(p + oa) == cls ? 1 : 0) | (__ldg(p + ob) == cls ? 2 : 0);
+            },
             [&](int rr, int cc) -> int { return __ldg(L + static_cast<long long>(rr) * W + cc) == cls ? 1 : 0; },
-            [&](uint32_t i, uint32_t v) { if (i < cap) out[i] = v; });
+            [&](int idx6) -> uint32_t { return s_step[idx6]; },
+            [&](uint32_t i, uint32_t v) {
+                // vertices leave in groups of four (one 16-byte store): the walk is bound by the number of
+                // per-lane memory transactions, not by bytes.  cap % 4 == 0, so a group is in or out as a whole.
+                const uint32_t ph = i & 3u;
+                if (ph == 3u) {
+                    if (i < cap) *reinterpret_cast<uint4*>(out + (i - 3u)) = make_uint4(g0, g1, g2, v);
+                } else {
+                    g0 = ph == 0u ? v : g0;
+                    g1 = ph == 1u ? v : g1;
+                    g2 = ph == 2u ? v : g2;
+                }
+            });
         npts = r.npts;
+        for (uint32_t i = npts & ~3u; i < npts; ++i)       // the last, incomplete group
+            if (i < cap) out[i] = (i & 3u) == 0u ? g0 : ((i & 3u) == 1u ? g1 : g2);
         closed = r.closed;
         overflow = npts > cap;
     }
@@ -78,6 +121,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
     if (closed) f |= m ? OCTM_CF_PRED_CLOSED : OCTM_CF_TRUE_CLOSED;
     if (overflow) f |= m ? OCTM_CF_PRED_OVERFLOW : OCTM_CF_TRUE_OVERFLOW;
     if (f) atomicOr(&prm.flags[item * K + cls], f);
+    }
 }
 
 // ------------------------------------------------------------------------------ first occurrence
@@ -391,16 +435,38 @@ __global__ void __launch_bounds__(kDistThreads) distance_kernel(const DistParams
     }
 }
 
-// ------------------------------------------------------------------------------ cooperative search
-// Default distance kernel.  A warp owns 32 CONSECUTIVE query vertices (adjacent on their polyline, so
-// they share almost the same neighbourhood of the other contour):
-//   1. box phase, shared by the warp: each lane tests a different source box (16 consecutive source
-//      vertices) against the bounding box of the 32 queries; a ballot yields the candidate boxes;
-//   2. each candidate is re-tested per lane against the lane's own best (one vote decides for the
-//      warp), then scanned by all lanes together: the source vertex is one broadcast LDS.128 and every
-//      lane folds it into its own minimum -- no divergence, 2 IMAD + 1 IMNMX per (query, vertex).
-// The minimum is exact: a box is skipped only when its lower bound cannot beat any lane's best.
-constexpr int kCoopThreads = 256;
+// ------------------------------------------------------------------------------ tiled search + select
+// Default path.  Two kernels, neither of which waits at a CTA barrier inside its hot loop:
+//
+//   distance_search_kernel   one CTA per (item, class, direction).  The source contour is staged in
+//       shared memory in tiles of `tile` vertices as int4 {y, x, y^2+x^2, -} with one bounding box per
+//       16 consecutive vertices (consecutive in trace order => compact).  A warp owns 32 CONSECUTIVE
+//       query vertices (adjacent on their polyline, so they share almost the same neighbourhood of
+//       the other contour):
+//         1. box phase, shared by the warp: each lane tests a different source box against the
+//            bounding box of the 32 queries; a ballot yields the candidate boxes;
+//         2. each candidate is re-tested per lane against the lane's own best (one vote decides for
+//            the warp), then scanned by all lanes together: the source vertex is one broadcast LDS.128
+//            and every lane folds it into its own minimum -- 2 IMAD + 1 IMNMX per (query, vertex).
+//       The minimum is exact: a box is skipped only when its lower bound cannot beat any lane's best.
+//       Squared distances go to the d2 scratch in global memory (4 B per query vertex); contours of
+//       any length are handled tile by tile, the running minimum carried in that scratch.
+//   distance_select_kernel   one WARP per (item, class, direction): max, sum of sqrt(D2/4) in float64
+//       (fixed order), and the two order statistics of numpy's linear 95th percentile by an 8-bit
+//       radix select whose histogram updates are aggregated with MATCH.ANY (no atomics, no barriers).
+constexpr int kSearchThreads = 256;
+#ifndef OCTM_SEARCH_MINB
+#define OCTM_SEARCH_MINB 6
+#endif
+
+struct SearchParams {
+    const uint32_t* verts;   // [n][K][2][max_pts]
+    const uint32_t* n_pts;   // [n][K][2]
+    long long n_units;       // n * K * 2
+    int max_pts;
+    int tile;                // source vertices staged per pass, multiple of kBox
+    uint32_t* d2;            // [n][K][2][max_pts]
+};
 
 __device__ __forceinline__ void coop_scan_box(const int4* src4, int bb, int ns, int cy, int cx, int& bm) {
     const int i0 = bb * kBox;
@@ -418,43 +484,37 @@ __device__ __forceinline__ void coop_scan_box(const int4* src4, int bb, int ns, 
     }
 }
 
-__global__ void __launch_bounds__(kCoopThreads) distance_coop_kernel(const DistParams prm) {
+__global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_search_kernel(const SearchParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_scr[8];
-    __shared__ double s_dscr[8];
-    __shared__ uint32_t s_bc[2];
-    const int cap = prm.max_pts;
-    int4* const src4 = reinterpret_cast<int4*>(dsm);                                        // {y, x, y^2+x^2, -}
-    uint32_t* const d2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(cap) * 16);
-    int4* const boxes = reinterpret_cast<int4*>(dsm + static_cast<size_t>(cap) * 20);      // {ymin, ymax, xmin, xmax}
+    const int cap = prm.max_pts, tile = prm.tile;
+    int4* const src4 = reinterpret_cast<int4*>(dsm);                                          // {y, x, y^2+x^2, -}
+    int4* const boxes = reinterpret_cast<int4*>(dsm + static_cast<size_t>(tile) * 16);       // {ymin, ymax, xmin, xmax}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
-        const uint32_t n0 = prm.n_pts[pair * 2 + 0], n1 = prm.n_pts[pair * 2 + 1];
-        const int n[2] = {static_cast<int>(min(n0, (uint32_t)cap)), static_cast<int>(min(n1, (uint32_t)cap))};
-        if (n[0] == 0 || n[1] == 0) {
-            if (threadIdx.x < 2) {
-                prm.max_sq[pair * 2 + threadIdx.x] = 0;
-                prm.p95_sq[pair * 4 + threadIdx.x * 2] = prm.p95_sq[pair * 4 + threadIdx.x * 2 + 1] = 0;
-                prm.sum_dist[pair * 2 + threadIdx.x] = 0.0;
-            }
-            continue;
-        }
+    for (long long unit = blockIdx.x; unit < prm.n_units; unit += gridDim.x) {
+        const long long pair = unit >> 1;
+        const int dir = static_cast<int>(unit & 1);
         // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
-        for (int dir = 0; dir < 2; ++dir) {
-            const int ns = n[dir], nq = n[1 - dir];
-            const uint32_t* vs = prm.verts + (pair * 2 + dir) * static_cast<long long>(cap);
-            const uint32_t* vq = prm.verts + (pair * 2 + 1 - dir) * static_cast<long long>(cap);
-            __syncthreads();
-            for (int i = threadIdx.x; i < ns; i += kCoopThreads) {
-                const uint32_t v = vs[i];
+        const int ns_all = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
+        const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
+        if (ns_all == 0 || nq == 0) continue;
+        const uint32_t* vs = prm.verts + (pair * 2 + dir) * static_cast<long long>(cap);
+        const uint32_t* vq = prm.verts + (pair * 2 + 1 - dir) * static_cast<long long>(cap);
+        uint32_t* dq = prm.d2 + unit * static_cast<long long>(cap);
+        const float ratio = static_cast<float>(ns_all) / static_cast<float>(nq);
+        const int nchunks = (nq + 31) >> 5;
+
+        for (int t0 = 0; t0 < ns_all; t0 += tile) {
+            const int ns = min(tile, ns_all - t0);
+            const int nb = (ns + kBox - 1) / kBox;
+            __syncthreads();                       // every warp is done with the previous tile
+            for (int i = threadIdx.x; i < ns; i += kSearchThreads) {
+                const uint32_t v = vs[t0 + i];
                 const int y = v >> 16, x = v & 0xffff;
                 src4[i] = make_int4(y, x, y * y + x * x, 0);
             }
             __syncthreads();
-            const int nb = (ns + kBox - 1) / kBox;
-            for (int b = threadIdx.x; b < nb; b += kCoopThreads) {
+            for (int b = threadIdx.x; b < nb; b += kSearchThreads) {
                 int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
                 const int e = min(ns, (b + 1) * kBox);
                 for (int i = b * kBox; i < e; ++i) {
@@ -464,21 +524,28 @@ __global__ void __launch_bounds__(kCoopThreads) distance_coop_kernel(const DistP
                 boxes[b] = make_int4(ymin, ymax, xmin, xmax);
             }
             __syncthreads();
-            const float ratio = static_cast<float>(ns) / static_cast<float>(nq);
-            const int nchunks = (nq + 31) >> 5;
-            for (int c = warp; c < nchunks; c += kCoopThreads / 32) {
+            for (int c = warp; c < nchunks; c += kSearchThreads / 32) {
                 const int j = c * 32 + lane;
                 const uint32_t v = vq[min(j, nq - 1)];          // tail lanes repeat the last query
                 const int qy = v >> 16, qx = v & 0xffff;
                 const int cy = -2 * qy, cx = -2 * qx, qn = qy * qy + qx * qx;
                 const int q_ymin = __reduce_min_sync(0xffffffffu, qy), q_ymax = __reduce_max_sync(0xffffffffu, qy);
                 const int q_xmin = __reduce_min_sync(0xffffffffu, qx), q_xmax = __reduce_max_sync(0xffffffffu, qx);
-                // prime every lane's bound with the box at the same relative position along the other contour
-                const int bg = min(ns - 1, static_cast<int>(static_cast<float>(c * 32 + 16) * ratio)) / kBox;
-                int bm = 0x7fffffff;
-                coop_scan_box(src4, bg, ns, cy, cx, bm);
-                int bestd = bm + qn;
+                // prime every lane's bound: first tile -> the box at the same relative position along the other
+                // contour (clamped into the tile); later tiles -> the minimum over the tiles before
+                int bg = -1, bm, bestd;
+                if (t0 == 0) {
+                    bg = min(min(ns_all - 1, static_cast<int>(static_cast<float>(c * 32 + 16) * ratio)) / kBox, nb - 1);
+                    bm = 0x7fffffff;
+                    coop_scan_box(src4, bg, ns, cy, cx, bm);
+                    bestd = bm + qn;
+                } else {
+                    bestd = static_cast<int>(dq[min(j, nq - 1)]);
+                    bm = bestd - qn;
+                }
                 int bmax = __reduce_max_sync(0xffffffffu, bestd);
+                // box phase, shared by the warp: each lane tests a different source box against the bounding
+                // box of the 32 queries; candidates are then re-tested per lane and scanned by all lanes
                 for (int b0 = 0; b0 < nb; b0 += 32) {
                     const int b = b0 + lane;
                     bool cand = false;
@@ -499,44 +566,142 @@ __global__ void __launch_bounds__(kCoopThreads) distance_coop_kernel(const DistP
                     }
                     bmax = __reduce_max_sync(0xffffffffu, bestd);
                 }
-                if (j < nq) d2[j] = static_cast<uint32_t>(bestd);
-            }
-            __syncthreads();
-            // K7: max, sum of sqrt, two order statistics
-            uint32_t vmax = 0;
-            double dsum = 0.0;
-            for (int j = threadIdx.x; j < nq; j += kCoopThreads) {
-                const uint32_t v = d2[j];
-                vmax = max(vmax, v);
-                dsum += sqrt(static_cast<double>(v) / 4.0);
-            }
-            vmax = block_reduce_max<kCoopThreads>(vmax, s_scr);
-            dsum = block_reduce_add<kCoopThreads>(dsum, s_dscr);
-            const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);
-            const uint32_t lo = static_cast<uint32_t>(floor(pos));
-            const uint32_t v_lo = block_select<kCoopThreads>(d2, nq, lo, vmax, s_hist, s_bc);
-            uint32_t cnt_le = 0, next_gt = 0xffffffffu;
-            for (int j = threadIdx.x; j < nq; j += kCoopThreads) {
-                const uint32_t v = d2[j];
-                cnt_le += v <= v_lo ? 1u : 0u;
-                if (v > v_lo) next_gt = min(next_gt, v);
-            }
-            cnt_le = block_reduce_add<kCoopThreads>(cnt_le, s_scr);
-            next_gt = block_reduce_min<kCoopThreads>(next_gt, s_scr);
-            const uint32_t v_hi = (lo + 1 >= static_cast<uint32_t>(nq) || cnt_le >= lo + 2) ? v_lo : next_gt;
-            if (prm.sq_out != nullptr) {
-                uint32_t* o = prm.sq_out + (pair * 2 + dir) * static_cast<long long>(cap);
-                for (int j = threadIdx.x; j < nq; j += kCoopThreads) o[j] = d2[j];
-            }
-            if (threadIdx.x == 0) {
-                prm.max_sq[pair * 2 + dir] = vmax;
-                prm.p95_sq[pair * 4 + dir * 2 + 0] = v_lo;
-                prm.p95_sq[pair * 4 + dir * 2 + 1] = v_hi;
-                prm.sum_dist[pair * 2 + dir] = dsum;
+                if (j < nq) dq[j] = static_cast<uint32_t>(bestd);
             }
         }
     }
 }
+
+struct SelectParams {
+    const uint32_t* n_pts;   // [n][K][2]
+    const uint32_t* d2;      // [n][K][2][max_pts]
+    long long n_units;
+    int max_pts;
+    uint32_t* max_sq;        // [n][K][2]
+    uint32_t* p95_sq;        // [n][K][2][2]
+    double* sum_dist;        // [n][K][2]
+};
+
+// k-th smallest (0-based) of vals[0..m): 8-bit radix passes over a warp-private histogram; every lane
+// returns the value.  Equal digits inside one 32-value slice are merged with MATCH.ANY, so the
+// histogram update is one plain read-modify-write per distinct digit.
+__device__ uint32_t warp_select(const uint32_t* vals, int m, uint32_t k, uint32_t vmax, uint32_t* hist /*256*/, int lane) {
+    uint32_t prefix = 0, maskbits = 0;
+    int shift = vmax >= (1u << 24) ? 24 : (vmax >= (1u << 16) ? 16 : (vmax >= (1u << 8) ? 8 : 0));
+    for (; shift >= 0; shift -= 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hist[i * 32 + lane] = 0;
+        __syncwarp();
+        for (int j0 = 0; j0 < m; j0 += 32) {
+            const int j = j0 + lane;
+            const uint32_t v = j < m ? vals[j] : 0u;
+            const bool ok = j < m && (v & maskbits) == prefix;
+            const uint32_t d = (v >> shift) & 255u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : 256u + lane);
+            if (ok && lane == __ffs(peers) - 1) hist[d] += __popc(peers);
+            __syncwarp();
+        }
+        uint32_t c[8], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; tot += c[i]; }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        const uint32_t excl = incl - tot;
+        const bool mine = k >= excl && k < incl;                 // exactly one lane
+        uint32_t digit = 0, knew = 0;
+        if (mine) {
+            uint32_t run = excl;
+            int d = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (k >= run + c[i]) { run += c[i]; d = i + 1; }
+                else break;
+            }
+            digit = static_cast<uint32_t>(lane * 8 + d);
+            knew = k - run;
+        }
+        const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+        digit = __shfl_sync(0xffffffffu, digit, src);
+        k = __shfl_sync(0xffffffffu, knew, src);
+        prefix |= digit << shift;
+        maskbits |= 255u << shift;
+        __syncwarp();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(128) distance_select_kernel(const SelectParams prm) {
+    __shared__ uint32_t s_hist[4][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cap = prm.max_pts;
+    for (long long unit = static_cast<long long>(blockIdx.x) * 4 + warp; unit < prm.n_units;
+         unit += static_cast<long long>(gridDim.x) * 4) {
+        const long long pair = unit >> 1;
+        const int dir = static_cast<int>(unit & 1);
+        const int ns = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
+        const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
+        if (ns == 0 || nq == 0) {
+            if (lane == 0) {
+                prm.max_sq[unit] = 0;
+                prm.p95_sq[unit * 2] = prm.p95_sq[unit * 2 + 1] = 0;
+                prm.sum_dist[unit] = 0.0;
+            }
+            continue;
+        }
+        const uint32_t* dq = prm.d2 + unit * static_cast<long long>(cap);
+        uint32_t vmax = 0;
+        double dsum = 0.0;
+        {   // four loads in flight per lane; the partial sums are folded in a fixed order
+            double ds[4] = {0.0, 0.0, 0.0, 0.0};
+            int j = lane;
+            for (; j + 96 < nq; j += 128) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = dq[j + 32 * u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    vmax = max(vmax, v[u]);
+                    ds[u] += sqrt(static_cast<double>(v[u]) / 4.0);
+                }
+            }
+            double dt = 0.0;
+            for (; j < nq; j += 32) {
+                const uint32_t v = dq[j];
+                vmax = max(vmax, v);
+                dt += sqrt(static_cast<double>(v) / 4.0);
+            }
+            dsum = ((ds[0] + ds[1]) + (ds[2] + ds[3])) + dt;
+        }
+        vmax = __reduce_max_sync(0xffffffffu, vmax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        // numpy linear percentile: virtual index (m - 1) * 0.95, neighbours floor and floor + 1
+        const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);
+        const uint32_t lo = static_cast<uint32_t>(floor(pos));
+        const uint32_t v_lo = warp_select(dq, nq, lo, vmax, s_hist[warp], lane);
+        uint32_t cnt_le = 0, next_gt = 0xffffffffu;
+#pragma unroll 4
+        for (int j = lane; j < nq; j += 32) {
+            const uint32_t v = dq[j];
+            cnt_le += v <= v_lo ? 1u : 0u;
+            if (v > v_lo) next_gt = min(next_gt, v);
+        }
+        cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+        next_gt = __reduce_min_sync(0xffffffffu, next_gt);
+        const uint32_t v_hi = (lo + 1 >= static_cast<uint32_t>(nq) || cnt_le >= lo + 2) ? v_lo : next_gt;
+        if (lane == 0) {
+            prm.max_sq[unit] = vmax;
+            prm.p95_sq[unit * 2 + 0] = v_lo;
+            prm.p95_sq[unit * 2 + 1] = v_hi;
+            prm.sum_dist[unit] = dsum;
+        }
+    }
+}
+
 
 }  // namespace octm
 
@@ -548,7 +713,7 @@ static int check_shape(int64_t n, int H, int W, int K, int max_pts) {
     if (H > 8192 || W > 8192)
         return octm::fail(OCTM_ERR_UNSUPPORTED, "image side > 8192: squared lattice distances leave the int32 kernel range");
     if (static_cast<long long>(H) * W >= (1ll << 32) - 1) return octm::fail(OCTM_ERR_UNSUPPORTED, "H*W >= 2^32");
-    if (max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "max_pts must be >= 8");
+    if (max_pts < 8 || max_pts % 4 != 0) return octm::fail(OCTM_ERR_INVALID, "max_pts must be >= 8 and a multiple of 4");
     return OCTM_OK;
 }
 
@@ -575,7 +740,12 @@ extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_p
         return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
     octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags};
     const long long threads = n_items * num_classes * 2;
-    octm::trace_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(p);
+    static const int env_ctas = [] { const char* e = getenv("OCTM_TRACE_CTAS"); return e ? atoi(e) : 0; }();
+    const int ctas_per_sm = env_ctas > 0 ? env_ctas : 6;
+    long long grid = (threads + 127) / 128;
+    const long long cap = static_cast<long long>(octm::sm_count()) * ctas_per_sm;
+    if (grid > cap) grid = cap;
+    octm::trace_kernel<<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
     return octm::check_launch("trace_kernel");
 }
 
@@ -586,37 +756,55 @@ static size_t dist_smem(int max_pts) {
 
 extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
                                        int max_pts, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
-                                       uint32_t* sq_out, void* stream) {
+                                       uint32_t* d2, void* stream) {
     if (n_items < 0 || num_classes < 1 || max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "bad shape");
     if (n_items == 0) return OCTM_OK;
     if (!verts || !n_pts || !max_sq || !p95_sq || !sum_dist) return octm::fail(OCTM_ERR_INVALID, "null pointer");
-    const size_t smem = dist_smem(max_pts);
-    if (smem > static_cast<size_t>(octm::max_optin_smem()) - 4096)
-        return octm::fail(OCTM_ERR_UNSUPPORTED, "max_pts %d needs %zu B of shared memory", max_pts, smem);
-    // OCTM_DISTANCE_MODE = coop (default) | lane (per-lane pruned search) | brute (no pruning); all three
-    // produce identical integers (tests run the suite under each).
+    // OCTM_DISTANCE_MODE = tiled (default: search kernel + select kernel) | lane (per-lane pruned search,
+    // one kernel) | brute (no pruning, one kernel); all three produce identical integers (tests run each).
     static const int mode = [] {
         const char* e = getenv("OCTM_DISTANCE_MODE");
         if (e && !strcmp(e, "brute")) return 2;
         if (e && !strcmp(e, "lane")) return 1;
         return 0;
     }();
-    octm::DistParams p{verts, n_pts, n_items * num_classes, max_pts, max_sq, p95_sq, sum_dist, sq_out};
-    long long grid = n_items * num_classes;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n_pairs = n_items * num_classes;
+    if (mode == 0) {
+        if (d2 == nullptr) return octm::fail(OCTM_ERR_INVALID, "d2 scratch [n][K][2][max_pts] is required");
+        static const int env_tile = [] { const char* e = getenv("OCTM_DIST_TILE"); return e ? atoi(e) : 0; }();
+        int tile = env_tile >= octm::kBox ? (env_tile / octm::kBox) * octm::kBox : 2048;
+        if (tile > ((max_pts + octm::kBox - 1) / octm::kBox) * octm::kBox) tile = ((max_pts + octm::kBox - 1) / octm::kBox) * octm::kBox;
+        const size_t smem = static_cast<size_t>(tile) * 16 + static_cast<size_t>(tile / octm::kBox) * 16;
+        if (smem > static_cast<size_t>(octm::max_optin_smem()))
+            return octm::fail(OCTM_ERR_UNSUPPORTED, "tile %d needs %zu B of shared memory", tile, smem);
+        if (cudaFuncSetAttribute(octm::distance_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)) != cudaSuccess)
+            return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_search_kernel) failed");
+        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2};
+        long long grid = n_pairs * 2;
+        const long long cap = static_cast<long long>(octm::sm_count()) * 32;
+        if (grid > cap) grid = cap;
+        octm::distance_search_kernel<<<static_cast<unsigned>(grid), octm::kSearchThreads, smem, st>>>(sp);
+        if (int e = octm::check_launch("distance_search_kernel")) return e;
+        octm::SelectParams kp{n_pts, d2, n_pairs * 2, max_pts, max_sq, p95_sq, sum_dist};
+        long long kgrid = (n_pairs * 2 + 3) / 4;
+        const long long kcap = static_cast<long long>(octm::sm_count()) * 16;
+        if (kgrid > kcap) kgrid = kcap;
+        octm::distance_select_kernel<<<static_cast<unsigned>(kgrid), 128, 0, st>>>(kp);
+        return octm::check_launch("distance_select_kernel");
+    }
+    const size_t smem = dist_smem(max_pts);
+    if (smem > static_cast<size_t>(octm::max_optin_smem()) - 4096)
+        return octm::fail(OCTM_ERR_UNSUPPORTED, "max_pts %d needs %zu B of shared memory in this mode", max_pts, smem);
+    octm::DistParams p{verts, n_pts, n_pairs, max_pts, max_sq, p95_sq, sum_dist, d2};
+    long long grid = n_pairs;
     const long long cap = static_cast<long long>(octm::sm_count()) * 16;
     if (grid > cap) grid = cap;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mode == 0) {
-        if (cudaFuncSetAttribute(octm::distance_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 octm::max_optin_smem() - 4096) != cudaSuccess)
-            return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_coop_kernel) failed");
-        octm::distance_coop_kernel<<<static_cast<unsigned>(grid), octm::kCoopThreads, smem, st>>>(p);
-    } else {
-        auto kern = mode == 2 ? octm::distance_kernel<false> : octm::distance_kernel<true>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, octm::max_optin_smem() - 4096) != cudaSuccess)
-            return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
-        kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, st>>>(p);
-    }
+    auto kern = mode == 2 ? octm::distance_kernel<false> : octm::distance_kernel<true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, octm::max_optin_smem() - 4096) != cudaSuccess)
+        return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
+    kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, st>>>(p);
     return octm::check_launch("distance_kernel");
 }
 
@@ -625,7 +813,8 @@ extern "C" size_t octm_contour2d_workspace_bytes(int64_t n_items, int H, int W, 
     if (n_items <= 0 || num_classes < 1 || max_pts < 1) return 0;
     const size_t verts = static_cast<size_t>(n_items) * num_classes * 2 * max_pts * sizeof(uint32_t);
     const size_t first = static_cast<size_t>(n_items) * 2 * num_classes * sizeof(uint32_t);
-    return ((verts + 255) & ~static_cast<size_t>(255)) + ((first + 255) & ~static_cast<size_t>(255));
+    // vertices, squared-distance scratch (same shape), first occurrences
+    return 2 * ((verts + 255) & ~static_cast<size_t>(255)) + ((first + 255) & ~static_cast<size_t>(255));
 }
 
 extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
@@ -639,7 +828,8 @@ extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
                           octm_contour2d_workspace_bytes(n_items, H, W, num_classes, max_pts));
     uint32_t* verts = static_cast<uint32_t*>(workspace);
     const size_t verts_b = (static_cast<size_t>(n_items) * num_classes * 2 * max_pts * sizeof(uint32_t) + 255) & ~static_cast<size_t>(255);
-    uint32_t* fp_ws = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + verts_b);
+    uint32_t* d2_ws = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + verts_b);
+    uint32_t* fp_ws = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + 2 * verts_b);
     if (first_pos == nullptr) {
         // no label pass ran: find the first occurrences of both maps here, interleaved [n][2][K]
         const long long grid = n_items < 148 * 8 ? n_items : 148 * 8;
@@ -655,5 +845,5 @@ extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
     if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, max_pts, verts, n_pts,
                                         flags, stream))
         return e;
-    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, max_sq, p95_sq, sum_dist, nullptr, stream);
+    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, max_sq, p95_sq, sum_dist, d2_ws, stream);
 }

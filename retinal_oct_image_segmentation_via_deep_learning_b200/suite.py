@@ -19,8 +19,8 @@ import torch
 from . import _lib, derive
 
 DEFAULT_MAX_PTS = 2048       # contour vertices kept per (item, class, map) on the first attempt
-MAX_MAX_PTS = 10000          # shared-memory bound of the distance kernel (~22.3 B per vertex)
-CONTOUR_CHUNK_BYTES = 1 << 30
+MAX_MAX_PTS = 1 << 16        # bound of the retry for items whose contour overflowed max_pts (8 B of scratch per vertex)
+CONTOUR_CHUNK_BYTES = 4 << 30   # vertex + squared-distance scratch per chunk of items (grow-only, reused)
 
 
 def _ptr(t):
@@ -169,25 +169,26 @@ def _vertex_scratch(dev, numel):
 
 def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None):
     n, h, w = yt.shape
+    max_pts = (int(max_pts) + 3) & ~3          # vertices are stored in 16-byte groups
     dev = yt.device
     i32 = dict(dtype=torch.int32, device=dev)
-    if want_verts:
-        verts = torch.empty((n, k, 2, max_pts), **i32)
-    else:       # stream-ordered reuse: every consumer of the scratch is enqueued on the same stream
-        verts = _vertex_scratch(dev, n * k * 2 * max_pts).view(n, k, 2, max_pts)
+    numel = n * k * 2 * max_pts
+    # stream-ordered reuse: every consumer of the scratch is enqueued on the same stream
+    scratch = None if (want_verts and want_sq) else _vertex_scratch(dev, 2 * numel)
+    verts = torch.empty((n, k, 2, max_pts), **i32) if want_verts else scratch[:numel].view(n, k, 2, max_pts)
+    sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else scratch[numel:].view(n, k, 2, max_pts)
     n_pts = torch.empty((n, k, 2), **i32)
     flags = torch.empty((n, k), **i32)
     max_sq = torch.empty((n, k, 2), **i32)
     p95 = torch.empty((n, k, 2, 2), **i32)
     sums = torch.empty((n, k, 2), dtype=torch.float64, device=dev)
-    sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else None
     with _Timed(timers, "contour_trace"):
         _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), max_pts, _ptr(verts),
                   _ptr(n_pts), _ptr(flags), _stream())
     with _Timed(timers, "contour_distance"):
         _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, _ptr(max_sq), _ptr(p95),
                   _ptr(sums), _ptr(sq), _stream())
-    return ContourOut(n_pts, flags, max_sq, p95, sums, verts if want_verts else None, sq, max_pts)
+    return ContourOut(n_pts, flags, max_sq, p95, sums, verts if want_verts else None, sq if want_sq else None, max_pts)
 
 
 def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
@@ -199,6 +200,7 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
     yt, yp = _check_pair(y_true, y_pred)
     n, h, w = yt.shape
     k = int(num_classes)
+    max_pts = (int(max_pts) + 3) & ~3
     if h < 2 or w < 2:
         raise ValueError("Input array must be at least 2x2.")     # skimage's message for find_contours
     dev = yt.device
@@ -210,7 +212,7 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
                 _lib.call("octm_first_pos_u8", _ptr(src), n, h * w, k, _ptr(tmp), _stream())
                 first_pos[:, m, :] = tmp
         keep = return_vertices or return_sq
-        per_item = k * 2 * max_pts * 4 * (2 if return_sq else 1)
+        per_item = k * 2 * max_pts * 4 * 2          # vertices + squared-distance scratch
         chunk = n if keep else max(1, min(n, CONTOUR_CHUNK_BYTES // per_item))
         parts = []
         for s in range(0, n, chunk):
@@ -240,8 +242,7 @@ def _retry_overflow(out, yt, yp, k, first_pos, keep=False):
     redo = _contour_chunk(yt[idx].contiguous(), yp[idx].contiguous(), k, first_pos[idx].contiguous(), big, False, False)
     still = (redo.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0
     if bool(still.any()):
-        raise _lib.OctmError(f"a contour has more than {big} vertices: not supported by the "
-                             "shared-memory distance kernel")
+        raise _lib.OctmError(f"a contour has more than {big} vertices: pass a larger max_pts")
     for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist"):
         getattr(out, f)[idx] = getattr(redo, f)
     return True

@@ -1,5 +1,5 @@
-"""GPU parity: the three distance-search strategies (cooperative boxes, per-lane boxes, brute force)
-return identical squared distances -- pruning never changes a result."""
+"""GPU parity: the distance-search strategies (tiled cooperative boxes + select kernel, per-lane boxes,
+brute force) return identical squared distances -- pruning and tiling never change a result."""
 import json
 import os
 import subprocess
@@ -31,8 +31,10 @@ print(json.dumps(out))
 """ % ROOT
 
 
-def _run(mode):
+def _run(mode, tile=None):
     env = dict(os.environ, OCTM_DISTANCE_MODE=mode)
+    if tile is not None:
+        env["OCTM_DIST_TILE"] = str(tile)
     r = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     return json.loads(r.stdout.strip().splitlines()[-1])
@@ -40,5 +42,6 @@ def _run(mode):
 
 def test_all_modes_agree(cuda):
     ref = _run("brute")
-    assert _run("coop") == ref
+    assert _run("tiled") == ref
+    assert _run("tiled", tile=64) == ref        # contours span many source tiles
     assert _run("lane") == ref
