@@ -40,43 +40,89 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs.
+
+    In-process NVML (nvidia_ml_py) from a thread, one cheap query every 20 ms: an `nvidia-smi -lms` child
+    process holds the driver for milliseconds per query and was measured to stretch a 17 ms step to 18-27 ms.
+    Falls back to that child process only if NVML cannot be imported."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.thread, self.stop_flag = [], None, index, None, False
+        self.max_mhz, self.source = None, None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        if os.environ.get("OCTM_BENCH_NOCLOCKS") == "1":      # diagnosis only: is the sampler disturbing the run?
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [getattr(pynvml, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                                                    "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap")]
+            if not all(bits):
+                bits = [0x8, 0x40, 0x20, 0x4]            # NVML ABI values of the four reasons above
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.perf_counter(), mhz, [bool(r & b) for b in bits]))
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            c = [x.strip() for x in line.split(",")]
+            if c and c[0].isdigit():
+                if len(c) > 1 and c[1].isdigit():
+                    self.max_mhz = max(self.max_mhz or 0, int(c[1]))
+                self.rows.append((time.perf_counter(), int(c[0]), [len(c) > 2 + i and c[2 + i] == "Active" for i in range(4)]))
 
     def stop(self, t0=None, t1=None):
         """Summary of the samples taken inside [t0, t1] (perf_counter; all samples if none fall inside).
-        The process is started BEFORE the warm-up: nvidia-smi's own start-up (NVML init) stalls CUDA calls
-        for tens of milliseconds on a fresh box and must not land in the timed region."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 is None or t0 <= t <= t1 + 0.15]
-        if not rows:
-            rows = [r for _, r in self.rows]
-        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        Sampling starts BEFORE the warm-up so that its own initialisation is not in the timed region."""
+        if self.thread is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.05)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if t0 is None or t0 <= r[0] <= t1 + 0.05] or list(self.rows)
+        sm = sorted(r[1] for r in rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -152,14 +198,15 @@ def run_b200(args):
     trace = os.environ.get("OCTM_BENCH_TRACE") == "1"
 
     def step():
+        """One pass of the whole suite over this rank's batch, enqueued asynchronously: kernels, the totals
+        kernel and the cross-rank all-reduce.  Results stay in HBM; they are read back after the timed region
+        (a per-step read-back would put this host's scheduling jitter, not the GPU, on the clock)."""
         t0 = time.perf_counter()
         res = suite.evaluate(yt, yp, K, contours=not args.no_contours, timers=timers)
-        t1 = time.perf_counter()
-        tot = odist.dataset_totals(res, world)          # one small all-reduce (no-op for world == 1)
+        pend = odist.dataset_totals_async(res, world)     # one small all-reduce on the device vector
         if trace:
-            print(f"[rank {rank}] launch {1e3 * (t1 - t0):.2f} ms, totals+allreduce+D2H {1e3 * (time.perf_counter() - t1):.2f} ms",
-                  file=sys.stderr)
-        return res, tot
+            print(f"[rank {rank}] enqueue {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
+        return pend
 
     def barrier():
         torch.cuda.synchronize()
@@ -172,23 +219,28 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.5)                      # let nvidia-smi finish initialising before anything is timed
     for _ in range(args.warmup):
-        step()
+        step().result()
     barrier()
     timers.clear()
     gc.collect()
     gc.disable()          # a generational collection inside a ~15 ms step is a 10 ms host stall
+    all_totals = torch.zeros((args.steps, int(_lib.load().octm_totals_len(K))), dtype=torch.float64, device=dev)
     launches0 = _lib.launch_count()
     t_begin = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        res, tot = step()
+    pend = None
+    for i in range(args.steps):
+        pend = step()                     # the previous step's outputs go back to torch's caching allocator here:
+        all_totals[i].copy_(pend.reduced) # no cudaMalloc in the timed region (one can stall the host for 50+ ms)
     ev1.record()
     barrier()
+    tot = pend.result()
+    tot_host = all_totals.cpu().numpy()
+    assert all((tot_host[i] == tot_host[0]).all() for i in range(args.steps)), "steps disagree on the dataset totals"
     ms = ev0.elapsed_time(ev1)
     gc.enable()
     launches = _lib.launch_count() - launches0
-    t_end = time.perf_counter()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -246,7 +298,8 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "items_per_gpu": n, "height": H, "width": W, "num_classes": K,
                        "contours": not args.no_contours, "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2"
-                       % (n * BYTES_PER_BSCAN / 1e9), "sharding": f"items x{world}, one NCCL all-reduce of totals"},
+                       % (n * BYTES_PER_BSCAN / 1e9), "sharding": f"items x{world}, one NCCL all-reduce of totals",
+                       "results": "left in HBM during the timed region; every step's dataset totals are read back and compared after it"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernel_ms_per_step": kern,
             "dataset_dice": [float(x) for x in tot["dice_coefficient"]] if tot else None,

@@ -157,6 +157,21 @@ class ContourOut:
 _SCRATCH = {}      # device -> grow-only int32 scratch for contour vertices (pure workspace, never returned)
 
 
+_STAGING = {}      # device -> (copy stream, grow-only uint8 staging buffer of evaluate_host)
+
+
+def _staging(dev, nbytes):
+    """Copy stream and device staging buffer of ``evaluate_host``, cached per device: a fresh cudaMalloc of
+    a few hundred MB per call costs more than the copies it serves."""
+    ent = _STAGING.get(dev)
+    if ent is None or ent[1].numel() < nbytes:
+        stream = ent[0] if ent is not None else torch.cuda.Stream(device=dev)
+        _STAGING.pop(dev, None)
+        ent = (stream, torch.empty((nbytes,), dtype=torch.uint8, device=dev))
+        _STAGING[dev] = ent
+    return ent
+
+
 def _vertex_scratch(dev, numel):
     buf = _SCRATCH.get(dev)
     if buf is None or buf.numel() < numel:
@@ -420,9 +435,10 @@ def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, ch
         chunk_items = max(1, min(n, (256 << 20) // max(1, h * w)))       # ~256 MiB per map per buffer
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream()
-        copy = torch.cuda.Stream()
-        bufs = [(torch.empty((chunk_items, h, w), dtype=torch.uint8, device=dev),
-                 torch.empty((chunk_items, h, w), dtype=torch.uint8, device=dev)) for _ in range(2)]
+        copy, flat = _staging(dev, 4 * chunk_items * h * w)
+        copy.wait_stream(compute)           # earlier users of the (cached) staging buffers are done
+        views = flat[:4 * chunk_items * h * w].view(4, chunk_items, h, w)
+        bufs = [(views[0], views[1]), (views[2], views[3])]
         freed = [None, None]
         starts = list(range(0, n, chunk_items))
         ready = {}
@@ -443,6 +459,10 @@ def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, ch
         issue_copy(0)
         for ci, s0 in enumerate(starts):
             e0 = min(n, s0 + chunk_items)
+            if ci >= 1:
+                # chunk ci-1 still owns the staging buffer the next copy overwrites: settle it first (its
+                # overflow retry, if any, re-reads its inputs).  One ~1 KB read-back per chunk.
+                parts[ci - 1].totals_host()
             if ci + 1 < len(starts):
                 issue_copy(ci + 1)                               # overlaps the kernels launched below
             bt, bp = bufs[ci & 1]
@@ -451,6 +471,7 @@ def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, ch
             done = torch.cuda.Event()
             done.record(compute)
             freed[ci & 1] = done
+        parts[-1].totals_host()        # the staging buffers are shared with later calls: settle before returning
         return parts[0] if len(parts) == 1 else _cat_results(parts)
 
 
