@@ -151,6 +151,22 @@ OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pt
                             double* sum_dist, uint32_t* d2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Front end: model scores -> uint8 label map, argmax over the class dimension (what a user does between
+ * a model's forward() and the metric functions; every model of the reference returns
+ * (B, num_classes, H, W), e.g. SOTAS/Lesions_Segment/ReLayNet_2017.py:106-108).
+ *   scores        [n][K][plane_elems] (channels_last = 0, NCHW) or [n][plane_elems][K] (channels_last = 1)
+ *   dtype         OCTM_DTYPE_F32 / F16 / BF16
+ *   labels        uint8 [n][plane_elems]; first maximal class wins ties, NaN counts as maximal
+ *                 (numpy / torch argmax semantics) */
+#define OCTM_DTYPE_F32 0
+#define OCTM_DTYPE_F16 1
+#define OCTM_DTYPE_BF16 2
+#define OCTM_DTYPE_F64 3
+
+OCTM_API int octm_argmax_labels(const void* scores, int dtype, int64_t n_items, int num_classes,
+                       int64_t plane_elems, int channels_last, uint8_t* labels, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Float64 epilogue on the device.  class_metrics[i][c][m] (double [n][K][OCTM_NUM_CLASS_METRICS]) holds
  * the value the reference function OCTM_M_* returns for the masks (y_true == c, y_pred == c) of
  * item i, evaluated from the exact integers above with the reference's operation order

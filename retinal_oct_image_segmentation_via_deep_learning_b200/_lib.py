@@ -20,6 +20,7 @@ CLASS_METRICS = ("accuracy", "sensitivity", "cm_precision", "specificity", "dice
                  "region_precision", "recall", "mean_squared_error", "root_mean_squared_error", "mad",
                  "vascularity_index", "thickness_difference", "hausdorff_distance", "hausdorff_distance_95", "assd")
 BOUNDARY_METRICS = ("boundary_mse", "boundary_rmse", "boundary_mad")
+DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
 
 _c = ctypes
 _P = _c.c_void_p
@@ -42,6 +43,7 @@ SIGNATURES = {
     "octm_first_pos_u8": (_INT, [_P, _I64, _I64, _INT, _P, _P]),
     "octm_contour2d_trace_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _INT, _P, _P, _P, _P]),
     "octm_contour2d_distance": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P, _P]),
+    "octm_argmax_labels": (_INT, [_P, _INT, _I64, _INT, _I64, _INT, _P, _P]),
     "octm_totals_len": (_INT, [_INT]),
     "octm_derive_metrics": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P]),
 }

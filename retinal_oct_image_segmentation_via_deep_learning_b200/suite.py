@@ -475,6 +475,41 @@ def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, ch
         return parts[0] if len(parts) == 1 else _cat_results(parts)
 
 
+def labels_from_scores(scores, *, channels_last=False, out=None):
+    """Model scores -> ``uint8`` label map: argmax over the class dimension.
+
+    ``scores``: CUDA float32 / float16 / bfloat16 tensor ``[N, K, H, W]`` (what every model of the
+    reference returns) or ``[N, H, W, K]`` with ``channels_last=True``; logits or probabilities alike.
+    Ties go to the first maximal class and a NaN counts as maximal, as in numpy / torch ``argmax``."""
+    if not isinstance(scores, torch.Tensor) or not scores.is_cuda:
+        raise TypeError("scores must be a CUDA torch tensor")
+    if scores.dim() != 4:
+        raise ValueError("expected [N, K, H, W] (or [N, H, W, K] with channels_last=True) scores")
+    dt = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}.get(scores.dtype)
+    if dt is None:
+        raise TypeError(f"scores must be float32, float16 or bfloat16, got {scores.dtype}")
+    s = scores.contiguous()
+    if channels_last:
+        n, h, w, k = s.shape
+    else:
+        n, k, h, w = s.shape
+    if k > 256:
+        raise ValueError("more than 256 classes do not fit a uint8 label map")
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.uint8, device=s.device)
+    elif out.shape != (n, h, w) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != s.device:
+        raise ValueError("out must be a contiguous uint8 [N, H, W] tensor on the scores' device")
+    with torch.cuda.device(s.device):
+        _lib.call("octm_argmax_labels", _ptr(s), dt, n, k, h * w, 1 if channels_last else 0, _ptr(out), _stream())
+    return out
+
+
+def evaluate_scores(y_true, scores, num_classes=None, *, channels_last=False, **kw):
+    """``evaluate(y_true, argmax(scores), ...)`` with the argmax done by ``labels_from_scores``."""
+    k = scores.shape[-1 if channels_last else 1] if num_classes is None else int(num_classes)
+    return evaluate(y_true, labels_from_scores(scores, channels_last=channels_last), k, **kw)
+
+
 def validate_labels(labels, num_classes):
     """Raise ValueError if any label is >= num_classes (one reduction kernel + a 4-byte readback)."""
     t = (labels.view(torch.uint8) if labels.dtype == torch.bool else labels).contiguous()
