@@ -167,6 +167,21 @@ OCTM_API int octm_argmax_labels(const void* scores, int dtype, int64_t n_items, 
                        int64_t plane_elems, int channels_last, uint8_t* labels, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * auc_score (Metrics/ConfusionMatrix_based_metrics.py:65-84): area under the ROC curve of a score map
+ * against a binary truth mask, per item -- sklearn.metrics.roc_auc_score(y_true.flatten(),
+ * y_pred.flatten()) with ties between scores counted one half (exact 64-bit rank sums, one division).
+ *   y_true   uint8 [n][item_elems]   two distinct values: the larger one is the positive class
+ *   scores   [n][item_elems] of dtype OCTM_DTYPE_F32 / F16 / BF16 / F64
+ *   auc      double [n]
+ * As in the reference (`except ValueError: return 0.0`): more than two label values, or NaN / inf
+ * scores, give 0.0.  A single-class (or empty) y_true gives single_class_value: NaN reproduces
+ * scikit-learn >= 1.6 (warns), 0.0 the older versions (raise).  Scratch: octm_auc_workspace_bytes. */
+OCTM_API size_t octm_auc_workspace_bytes(int64_t n_items, int64_t item_elems, int dtype);
+OCTM_API int octm_auc_u8(const uint8_t* y_true, const void* scores, int dtype, int64_t n_items, int64_t item_elems,
+                double single_class_value, double* auc, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Float64 epilogue on the device.  class_metrics[i][c][m] (double [n][K][OCTM_NUM_CLASS_METRICS]) holds
  * the value the reference function OCTM_M_* returns for the masks (y_true == c, y_pred == c) of
  * item i, evaluated from the exact integers above with the reference's operation order

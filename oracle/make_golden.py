@@ -11,6 +11,8 @@
   (scikit-image is absent, so this part is self-generated: "parity unpinned"); it pins the CUDA
   path to the oracle across refactors, and the squared distances are cross-checked against
   ``scipy.ndimage.distance_transform_edt`` in the tests.
+* ``auc_golden.npz``      -- ``auc_score`` of the unmodified reference (scikit-learn of this image) on
+  smooth, heavily tied and degenerate score maps.
 * ``suite_golden.npz``    -- one reduced-size and one full-size B-scan per BASELINE config with all
   integer intermediates (confusion, thickness, boundaries).
 """
@@ -133,14 +135,62 @@ def make_suite():
     print("suite_golden.npz:", len(names), "cases")
 
 
+def auc_cases():
+    """(name, y_true mask, score map): smooth probabilities, heavy ties, float32/float64, edge cases."""
+    rng = np.random.default_rng(31)
+    cases = []
+    yt, _ = synth.lesion_pair(1, 64, 64, 4, seed=32)
+    m = (yt[0] > 0).astype(np.uint8)
+    logit = 3.0 * (m.astype(np.float64) - 0.5) + rng.normal(0, 1.5, m.shape)
+    cases.append(("lesion64_f64", m, 1.0 / (1.0 + np.exp(-logit))))
+    cases.append(("lesion64_f32", m, (1.0 / (1.0 + np.exp(-logit))).astype(np.float32)))
+    cases.append(("ties_quantised", m, np.round(1.0 / (1.0 + np.exp(-logit)), 1)))          # 11 distinct scores
+    cases.append(("binary_scores", m, (logit > 0).astype(np.float64)))                       # 2 distinct scores
+    cases.append(("constant_scores", m, np.full(m.shape, 0.5)))                              # one tie run -> 0.5
+    cases.append(("perfect", m, m.astype(np.float64) * 0.8 + 0.1))
+    cases.append(("inverted", m, 0.9 - m.astype(np.float64) * 0.8))
+    cases.append(("negative_and_zero", m, np.where(rng.random(m.shape) < 0.3, -0.0, logit)))  # -0.0 == +0.0 ties
+    yt2, yp2 = synth.layered_pair(1, 496, 512, 8, seed=33, noise=0.02)
+    m2 = (yt2[0] == 3).astype(np.uint8)
+    p2 = np.clip((yp2[0] == 3) * 0.7 + rng.random(m2.shape) * 0.3, 0, 1).astype(np.float32)
+    cases.append(("layer496x512_f32", m2, p2))
+    cases.append(("single_class", np.zeros((8, 8), np.uint8), rng.random((8, 8))))
+    cases.append(("three_labels", (rng.integers(0, 3, (8, 8))).astype(np.uint8), rng.random((8, 8))))
+    bad = rng.random((8, 8)); bad[2, 3] = np.nan
+    cases.append(("nan_score", (rng.random((8, 8)) < 0.5).astype(np.uint8), bad))
+    return cases
+
+
+def make_auc(ref):
+    import warnings
+    blob, names = {}, []
+    for name, m, p in auc_cases():
+        names.append(name)
+        blob[name + "/y_true"], blob[name + "/scores"] = m, p
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            blob[name + "/auc"] = np.float64(ref.auc_score(m, p))
+    import sklearn
+    blob["names"] = np.array(names)
+    blob["source"] = np.array(f"executed reference: {ref.root} with scikit-learn {sklearn.__version__}")
+    np.savez_compressed(os.path.join(OUT, "auc_golden.npz"), **blob)
+    print("auc_golden.npz:", len(names), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
     if ref is None:
         raise SystemExit("reference not found: run this in the build container")
-    make_counts(ref)
-    make_contours()
-    make_suite()
+    which = sys.argv[1:] or ["counts", "contours", "suite", "auc"]
+    if "counts" in which:
+        make_counts(ref)
+    if "contours" in which:
+        make_contours()
+    if "suite" in which:
+        make_suite()
+    if "auc" in which:
+        make_auc(ref)
 
 
 if __name__ == "__main__":

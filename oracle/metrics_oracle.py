@@ -56,6 +56,50 @@ def specificity(y_true, y_pred):
     return tn / (tn + fp + EPS)
 
 
+def auc_score(y_true, y_pred, single_class_value=float("nan")):
+    """ConfusionMatrix_based_metrics.py:65-84 -- ``roc_auc_score(y_true.flatten(), y_pred.flatten())``,
+    ``except ValueError: return 0.0``.
+
+    scikit-learn (unpinned by the reference; restated from ``sklearn/metrics/_ranking.py``:
+    ``_binary_clf_curve`` + ``roc_curve`` + ``auc``): stable sort by descending score, one ROC point per
+    DISTINCT score (tps = positives with score >= threshold, fps likewise), trapezoidal area of tpr
+    over fpr.  ValueError cases (-> 0.0): non-finite scores, more than two label values, length
+    mismatch, empty input.  A single-class y_true is the version-dependent case (>= 1.6: NaN + warning;
+    before: ValueError -> 0.0), hence ``single_class_value``."""
+    t = np.asarray(y_true).reshape(-1)
+    s = np.asarray(y_pred).reshape(-1).astype(np.float64)
+    if t.size != s.size or t.size == 0 or not np.all(np.isfinite(s)):
+        return 0.0
+    vals = np.unique(t)
+    if vals.size > 2:
+        return 0.0
+    if vals.size < 2:
+        return single_class_value
+    pos = (t == vals[-1]).astype(np.float64)
+    order = np.argsort(s, kind="mergesort")[::-1]
+    s_sorted, pos_sorted = s[order], pos[order]
+    distinct = np.where(np.diff(s_sorted))[0]
+    idx = np.r_[distinct, pos_sorted.size - 1]
+    tps = np.cumsum(pos_sorted)[idx]
+    fps = 1 + idx - tps
+    tps, fps = np.r_[0, tps], np.r_[0, fps]
+    fpr, tpr = fps / fps[-1], tps / tps[-1]
+    return float(np.trapezoid(tpr, fpr)) if hasattr(np, "trapezoid") else float(np.trapz(tpr, fpr))
+
+
+def auc_rank_sum(y_true, y_pred):
+    """The same area as an exact rational: (2 * Mann-Whitney U with ties counted one half, n_pos, n_neg)
+    as Python ints -- what the CUDA kernel accumulates before its single division."""
+    t = np.asarray(y_true).reshape(-1)
+    s = np.asarray(y_pred).reshape(-1).astype(np.float64)
+    vals = np.unique(t)
+    pos = t == vals[-1]
+    neg_scores = np.sort(s[~pos])
+    less = np.searchsorted(neg_scores, s[pos], side="left")
+    leq = np.searchsorted(neg_scores, s[pos], side="right")
+    return int(less.sum()) + int(leq.sum()), int(pos.sum()), int((~pos).sum())
+
+
 # ---------------------------------------------------------------- Region_based_metrics.py
 def dice_coefficient(y_true, y_pred):
     """Region_based_metrics.py:13-15 -- 2 I / (sum(t) + sum(p) + 1e-7)."""

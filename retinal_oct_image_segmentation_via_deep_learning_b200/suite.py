@@ -510,6 +510,37 @@ def evaluate_scores(y_true, scores, num_classes=None, *, channels_last=False, **
     return evaluate(y_true, labels_from_scores(scores, channels_last=channels_last), k, **kw)
 
 
+def auc_scores(y_true, scores, *, single_class_value=float("nan")):
+    """Per-item area under the ROC curve (``auc_score`` of the reference, batched): float64 ``[N]``.
+
+    ``y_true``: CUDA uint8 / bool ``[N, ...]`` binary masks; ``scores``: CUDA float16 / bfloat16 /
+    float32 / float64 tensor of the same shape.  Each item is flattened, as the reference does."""
+    for name, t in (("y_true", y_true), ("scores", scores)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise TypeError(f"{name} must be a CUDA torch tensor")
+    if y_true.dtype not in (torch.uint8, torch.bool):
+        raise TypeError("y_true must be uint8 or bool")
+    dt = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16,
+          torch.float64: _lib.DTYPE_F64}.get(scores.dtype)
+    if dt is None:
+        raise TypeError(f"scores must be a floating tensor, got {scores.dtype}")
+    if y_true.shape != scores.shape:
+        raise ValueError(f"shape mismatch: {tuple(y_true.shape)} vs {tuple(scores.shape)}")
+    yt = (y_true.view(torch.uint8) if y_true.dtype == torch.bool else y_true).contiguous()
+    sc = scores.contiguous()
+    n = yt.shape[0]
+    elems = yt[0].numel() if n else 0
+    out = torch.empty((n,), dtype=torch.float64, device=yt.device)
+    if n == 0:
+        return out
+    with torch.cuda.device(yt.device):
+        nbytes = int(_lib.load().octm_auc_workspace_bytes(n, elems, dt))
+        ws = _vertex_scratch(yt.device, (nbytes + 3) // 4 + 64)
+        _lib.call("octm_auc_u8", _ptr(yt), _ptr(sc), dt, n, elems, float(single_class_value), _ptr(out), _ptr(ws),
+                  ws.numel() * 4, _stream())
+    return out
+
+
 def validate_labels(labels, num_classes):
     """Raise ValueError if any label is >= num_classes (one reduction kernel + a 4-byte readback)."""
     t = (labels.view(torch.uint8) if labels.dtype == torch.bool else labels).contiguous()
