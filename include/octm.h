@@ -42,6 +42,12 @@ extern "C" {
 #define OCTM_ERR_LAUNCH (-3)      /* CUDA launch or attribute call failed */
 #define OCTM_ERR_WORKSPACE (-4)   /* workspace too small */
 
+/* element types of floating-point inputs (scores, probabilities, soft boundary positions) */
+#define OCTM_DTYPE_F32 0
+#define OCTM_DTYPE_F16 1
+#define OCTM_DTYPE_BF16 2
+#define OCTM_DTYPE_F64 3
+
 #define OCTM_MAX_CLASSES 16
 #define OCTM_NO_SEED 0xFFFFFFFFu
 
@@ -83,6 +89,18 @@ OCTM_API int octm_column_scan_u8(const uint8_t* y_true, const uint8_t* y_pred, i
  * (e.g. positions produced by a layer model): sum_sq[i][k], sum_abs[i][k] as int64 [n][Kb]. */
 OCTM_API int octm_boundary_error_i32(const int32_t* bnd_true, const int32_t* bnd_pred, int64_t n_items,
                             int num_boundaries, int W, int64_t* sum_sq, int64_t* sum_abs, void* stream);
+
+/* K3 on CONTINUOUS boundary positions (the soft-argmax rows LayerEngine.get_layer_positions produces,
+ * SOTAS/Layers_Segment/SD_Layer_Net/layer_engine.py:46-47): float64 sums of (a-b)^2 and |a-b| per
+ * (item, boundary) row, i.e. the numerators of mean_squared_error (PixelError_based_metrics.py:14-17) and
+ * mad (Contour_based_metrics.py:68-71) on float arrays [n][Kb][W] of dtype OCTM_DTYPE_*. */
+OCTM_API int octm_boundary_error_float(const void* bnd_true, const void* bnd_pred, int dtype, int64_t n_items,
+                              int num_boundaries, int64_t W, double* sum_sq, double* sum_abs, void* stream);
+
+/* Topology violations of boundary positions [n][Kb][W] (layer_engine.py:74-76, relu(pos[k] - pos[k+1])):
+ * sum_violation double [n][Kb-1], n_violations uint32 [n][Kb-1] (columns where boundary k lies below k+1). */
+OCTM_API int octm_topology_violations_float(const void* positions, int dtype, int64_t n_items, int num_boundaries,
+                                   int64_t W, double* sum_violation, uint32_t* n_violations, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused label pass: K1 + K2 + K3 + contour seeds in ONE read of both label tensors.
@@ -158,11 +176,6 @@ OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pt
  *   dtype         OCTM_DTYPE_F32 / F16 / BF16
  *   labels        uint8 [n][plane_elems]; first maximal class wins ties, NaN counts as maximal
  *                 (numpy / torch argmax semantics) */
-#define OCTM_DTYPE_F32 0
-#define OCTM_DTYPE_F16 1
-#define OCTM_DTYPE_BF16 2
-#define OCTM_DTYPE_F64 3
-
 OCTM_API int octm_argmax_labels(const void* scores, int dtype, int64_t n_items, int num_classes,
                        int64_t plane_elems, int channels_last, uint8_t* labels, void* stream);
 

@@ -30,5 +30,5 @@ def mad(y_true, y_pred):
     integer arrays (boundary positions) the boundary-error kernel."""
     if _dropin.is_binary_like(y_true) and _dropin.is_binary_like(y_pred):
         return np.float64(derive.count_metrics(*_dropin.binary_counts(y_true, y_pred))["mad"])
-    _, ab, n = _dropin.integer_error_sums(y_true, y_pred)
+    _, ab, n = _dropin.error_sums(y_true, y_pred)
     return np.float64(ab) / n if n else np.float64(np.nan)

@@ -2,7 +2,8 @@
 
 Binary masks go through the K=2 confusion kernel ((FP + FN) / size is exactly the reference's
 float mean); integer arrays such as ``(K-1, W)`` boundary positions go through
-``octm_boundary_error_i32`` (exact int64 sums, one float64 division).
+``octm_boundary_error_i32`` (exact int64 sums, one float64 division); floating arrays (soft boundary
+positions of a layer model) through ``octm_boundary_error_float`` (float64 sums, fixed order).
 """
 import numpy as np
 
@@ -13,7 +14,7 @@ def mean_squared_error(y_true, y_pred):
     """mean((y_true - y_pred)**2) -- reference PixelError_based_metrics.py:3-19."""
     if _dropin.is_binary_like(y_true) and _dropin.is_binary_like(y_pred):
         return np.float64(derive.count_metrics(*_dropin.binary_counts(y_true, y_pred))["mean_squared_error"])
-    sq, _, n = _dropin.integer_error_sums(y_true, y_pred)
+    sq, _, n = _dropin.error_sums(y_true, y_pred)
     return np.float64(sq) / n if n else np.float64(np.nan)
 
 

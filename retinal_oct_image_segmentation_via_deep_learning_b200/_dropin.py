@@ -59,33 +59,40 @@ def is_binary_like(a):
     return np.asarray(a).dtype in (np.bool_, np.uint8)
 
 
-def integer_error_sums(y_true, y_pred):
-    """(sum d^2, sum |d|, n) for two integer arrays (e.g. boundary positions) via the K3 kernel."""
-    def prep(a):
+def error_sums(y_true, y_pred):
+    """(sum d^2, sum |d|, n) for two arrays of any numeric dtype via the K3 kernels: exact int64 sums for
+    integer-valued data (masks, boundary indices), float64 sums for floating data (soft positions)."""
+    def to_t(a):
         if isinstance(a, torch.Tensor):
-            if a.is_floating_point():
-                r = a.round()
-                if not bool((r == a).all()):
-                    raise TypeError("non-integer float inputs are not supported on the GPU path yet")
-                a = r
-            return a.to(torch.int32).to(_device()).contiguous()
+            return a
         arr = np.asarray(a)
-        if arr.dtype.kind == "f":
-            if not np.array_equal(np.rint(arr), arr):
-                raise TypeError("non-integer float inputs are not supported on the GPU path yet")
-        elif arr.dtype.kind not in "iub":
+        if arr.dtype.kind not in "iubf":
             raise TypeError(f"unsupported dtype {arr.dtype}")
-        if arr.size and (arr.max() > 2**31 - 1 or arr.min() < -2**31):
-            raise ValueError("values do not fit int32")
-        return torch.from_numpy(np.ascontiguousarray(arr.astype(np.int32))).to(_device())
-    t, p = prep(y_true), prep(y_pred)
+        return torch.from_numpy(np.ascontiguousarray(arr))
+
+    t, p = to_t(y_true), to_t(y_pred)
     if t.shape != p.shape:
         raise ValueError(f"operands could not be broadcast together with shapes {tuple(t.shape)} {tuple(p.shape)}")
     n = t.numel()
     if n == 0:
         return np.int64(0), np.int64(0), 0
-    sq, ab = suite.boundary_error(t.reshape(1, 1, -1), p.reshape(1, 1, -1))
+    floating = t.is_floating_point() or p.is_floating_point()
+    if not floating:
+        for a in (t, p):
+            if a.dtype in (torch.int64, torch.uint64) and a.numel() and (int(a.max()) > 2**31 - 1 or int(a.min()) < -2**31):
+                floating = True                       # does not fit the int32 kernel: take the float64 route
+    dev = _device()
+    if floating:
+        t, p = t.to(torch.float64) if not t.is_floating_point() else t, p.to(torch.float64) if not p.is_floating_point() else p
+        sq, ab = suite.boundary_error(t.to(dev).reshape(1, 1, -1), p.to(dev).reshape(1, 1, -1))
+        return np.float64(sq.item()), np.float64(ab.item()), n
+    t = (t.view(torch.uint8) if t.dtype == torch.bool else t).to(torch.int32)
+    p = (p.view(torch.uint8) if p.dtype == torch.bool else p).to(torch.int32)
+    sq, ab = suite.boundary_error(t.to(dev).reshape(1, 1, -1), p.to(dev).reshape(1, 1, -1))
     return np.int64(sq.item()), np.int64(ab.item()), n
+
+
+integer_error_sums = error_sums          # former name
 
 
 def contour_scalars(y_true, y_pred):

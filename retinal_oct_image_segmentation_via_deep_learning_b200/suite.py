@@ -128,17 +128,61 @@ def confusion(y_true, y_pred, num_classes):
     return out
 
 
+_FLOAT_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16,
+                 torch.float64: _lib.DTYPE_F64}
+
+
 def boundary_error(bnd_true, bnd_pred):
-    """K3 alone on caller-supplied ``int32 [N, Kb, W]`` boundary positions -> (sum_sq, sum_abs) int64 [N, Kb]."""
+    """K3 alone on caller-supplied boundary positions ``[N, Kb, W]`` -> ``(sum_sq, sum_abs)`` per ``[N, Kb]`` row.
+
+    Integer positions (e.g. ``b_k(x)`` extracted from label maps) give exact int64 sums; floating
+    positions (the soft-argmax rows a layer model such as SD-LayerNet's ``LayerEngine`` produces) give
+    float64 sums accumulated in a fixed order."""
     if bnd_true.shape != bnd_pred.shape or bnd_true.dim() != 3:
         raise ValueError("expected two [N, Kb, W] tensors of equal shape")
+    n, kb, w = bnd_true.shape
+    if bnd_true.is_floating_point() or bnd_pred.is_floating_point():
+        dt = torch.promote_types(bnd_true.dtype, bnd_pred.dtype)
+        bt, bp = bnd_true.to(dt).contiguous(), bnd_pred.to(dt).contiguous()
+        sq = torch.empty((n, kb), dtype=torch.float64, device=bt.device)
+        ab = torch.empty((n, kb), dtype=torch.float64, device=bt.device)
+        with torch.cuda.device(bt.device):
+            _lib.call("octm_boundary_error_float", _ptr(bt), _ptr(bp), _FLOAT_DTYPES[dt], n, kb, w, _ptr(sq), _ptr(ab),
+                      _stream())
+        return sq, ab
     bt, bp = bnd_true.to(torch.int32).contiguous(), bnd_pred.to(torch.int32).contiguous()
-    n, kb, w = bt.shape
     sq = torch.empty((n, kb), dtype=torch.int64, device=bt.device)
     ab = torch.empty((n, kb), dtype=torch.int64, device=bt.device)
     with torch.cuda.device(bt.device):
         _lib.call("octm_boundary_error_i32", _ptr(bt), _ptr(bp), n, kb, w, _ptr(sq), _ptr(ab), _stream())
     return sq, ab
+
+
+def boundary_metrics(bnd_true, bnd_pred):
+    """``mean_squared_error`` / ``root_mean_squared_error`` / ``mad`` of the reference applied to every
+    boundary row: dict of float64 ``[N, Kb]`` CUDA tensors (reference: PixelError_based_metrics.py:14-35,
+    Contour_based_metrics.py:68-71)."""
+    sq, ab = boundary_error(bnd_true, bnd_pred)
+    w = bnd_true.shape[-1]
+    mse = sq.to(torch.float64) / w
+    return {"boundary_mse": mse, "boundary_rmse": torch.sqrt(mse), "boundary_mad": ab.to(torch.float64) / w}
+
+
+def topology_violations(positions):
+    """``relu(pos[:, :-1] - pos[:, 1:])`` of ``LayerEngine.get_topology_violations`` (SD_Layer_Net/layer_engine.py:74-76),
+    reduced over the width: ``(sum_violation float64 [N, Kb-1], n_violations int32 [N, Kb-1])``."""
+    if not isinstance(positions, torch.Tensor) or not positions.is_cuda or positions.dim() != 3:
+        raise TypeError("positions must be a CUDA tensor [N, Kb, W]")
+    pos = positions if positions.is_floating_point() else positions.to(torch.float64)
+    pos = pos.contiguous()
+    n, kb, w = pos.shape
+    if kb < 2:
+        raise ValueError("need at least two boundaries")
+    sv = torch.empty((n, kb - 1), dtype=torch.float64, device=pos.device)
+    nv = torch.empty((n, kb - 1), dtype=torch.int32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        _lib.call("octm_topology_violations_float", _ptr(pos), _FLOAT_DTYPES[pos.dtype], n, kb, w, _ptr(sv), _ptr(nv), _stream())
+    return sv, nv
 
 
 @dataclass
