@@ -111,6 +111,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// TMA 2-D tiled copy global -> shared through a tensor map (SASS: UTMALDG), completion on an mbarrier.
+// Out-of-range rows / columns of the box are filled with zeros and still count as transferred bytes.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int x, int y, uint32_t bar_smem, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::
+            "r"(dst_smem),
+        "l"(tmap), "r"(x), "r"(y), "r"(bar_smem), "l"(policy)
+        : "memory");
+}
+
+// mbarrier operations on raw shared-memory addresses (no generic -> shared conversion per call)
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parked_a(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!done);
+}
+
 // orders prior generic-proxy accesses to shared memory before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

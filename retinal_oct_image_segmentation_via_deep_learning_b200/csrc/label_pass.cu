@@ -26,6 +26,8 @@
 //     histograms -> K x K counts, one plain store per output element (no global atomics).
 //
 // GENERIC KERNEL: any H, W, K <= 16 (byte loads, shared-memory atomics).  Same outputs.
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -57,7 +59,7 @@ struct LabelPassParams {
 };
 
 // shared-memory carve-up of the fast kernel
-constexpr int kOffBars = 0;                    // full[8], empty[8]
+
 constexpr int kOffCounts = 128;                // u32[256]
 constexpr int kOffSq = kOffCounts + 1024;      // u64[16]
 constexpr int kOffAbs = kOffSq + 128;          // u64[16]
@@ -67,6 +69,7 @@ constexpr int kOffWarp = 2048;
 constexpr int kWarpTotals = 2 * 8 * kStrip * 2;    // u16 [map][thr][128]
 constexpr int kWarpHist = 64 * 32 * 2;             // u16 [code][lane]
 constexpr int kWarpQueue = kQueueCap * 16;         // uint4 entries
+constexpr int kWarpBars = 128;                     // the warp's S "stage full" mbarriers
 constexpr int kWarpBytesShort = kWarpHist + kWarpQueue;              // H <= 504: totals alias the histogram block
 constexpr int kWarpBytesTall = kWarpHist + kWarpQueue + kWarpTotals;
 constexpr int kShortRows = 504;   // 18 byte flushes x 7 nibble flushes x 4 rows
@@ -265,7 +268,9 @@ struct LaneState {
 };
 
 struct StageConsts {
-    uint32_t W2, W4, map_bytes, one;
+    uint32_t srow2, srow4;        // 2 / 4 rows of a staged strip in shared memory (bytes)
+    uint32_t W2, W4;              // 2 / 4 rows of the image (raster positions)
+    uint32_t map_bytes, one, all_classes;
     int phase, lane;
     bool colv;
     unsigned short* hist_lane;
@@ -282,20 +287,20 @@ template <int NP, bool CONF, bool COLS, bool SEEDS, bool FULL>
 __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint32_t pos, int rows, const StageConsts& sc) {
     const int npairs = (rows + 3) >> 2;
 #pragma unroll 1
-    for (int pr = 0; pr < npairs; ++pr, at += sc.W4, pos += sc.W4) {
+    for (int pr = 0; pr < npairs; ++pr, at += sc.srow4, pos += sc.W4) {
         uint2 tA, pA, tB, pB;
         bool va = true, vb = true;
         if (FULL) {
             tA = lds64(at);
-            tB = lds64(at + sc.W2);
+            tB = lds64(at + sc.srow2);
             pA = lds64(at + sc.map_bytes);
-            pB = lds64(at + sc.map_bytes + sc.W2);
+            pB = lds64(at + sc.map_bytes + sc.srow2);
         } else {
             va = sc.colv && 4 * pr + sc.phase < rows;
             vb = sc.colv && 4 * pr + sc.phase + 2 < rows;
             tA = make_uint2(kPadWord, kPadWord); pA = tA; tB = tA; pB = tA;
             if (va) { tA = lds64(at); pA = lds64(at + sc.map_bytes); }
-            if (vb) { tB = lds64(at + sc.W2); pB = lds64(at + sc.map_bytes + sc.W2); }
+            if (vb) { tB = lds64(at + sc.srow2); pB = lds64(at + sc.map_bytes + sc.srow2); }
         }
         if (COLS) {
             col_accumulate<NP>(ls.cs.nib[0], tA.x, pA.x, tB.x, pB.x, sc.one);
@@ -315,7 +320,7 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
                     // classes are tracked per WARP: rows only grow from pass to pass, so once any lane has
                     // met a class, later passes cannot hold an earlier pixel of it
                     uint32_t fresh = 0;
-                    if (changed || mixed_lane) {
+                    if ((changed || mixed_lane) && ls.warp_seen != sc.all_classes) {
                         const uint32_t bits = uni ? ((1u << ((b >> 3) & 7u)) | (0x100u << (b & 7u)))
                                                   : presence_bits(tA, pA, tB, pB);
                         fresh = bits & ~ls.warp_seen;
@@ -344,79 +349,85 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
     }
 }
 
+#ifndef OCTM_LP_MINB
+#define OCTM_LP_MINB 2
+#endif
+// Shared memory of the fast kernel: a fixed CTA block (kOffWarp bytes), then one private block per warp:
+//   [ S full-barriers, padded to 128 B | histogram 4 KB | queue 1 KB | (H > 504: column totals 4 KB) | ring ]
+// The ring is PRIVATE to the warp: S stages x 2 maps x R rows x strip bytes, filled by 2-D TMA tile copies
+// (one box of R rows x 128 columns per map) that the warp issues for itself.  Warps of a CTA therefore
+// never wait for each other inside an item; they meet only in the item epilogue.
 template <int NP, bool CONF, bool COLS, bool SEEDS, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 16 * 32 : 8 * 32, WIDE ? 1 : 2) label_pass_fast(const LabelPassParams prm) {
+__global__ void __launch_bounds__(WIDE ? 16 * 32 : 8 * 32, WIDE ? 1 : OCTM_LP_MINB)
+label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap tm_true, const __grid_constant__ CUtensorMap tm_pred) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NW = blockDim.x >> 5;
     const int H = prm.H, W = prm.W, K = prm.K, R = prm.R, S = prm.S;
 
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffBars);
-    uint64_t* empty = full + kMaxStages;
     uint32_t* cta_counts = reinterpret_cast<uint32_t*>(smem + kOffCounts);
     unsigned long long* cta_sq = reinterpret_cast<unsigned long long*>(smem + kOffSq);
     unsigned long long* cta_abs = reinterpret_cast<unsigned long long*>(smem + kOffAbs);
     unsigned long long* cta_thick = reinterpret_cast<unsigned long long*>(smem + kOffThick);
     uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + kOffFirst);
     const bool tall = H > kShortRows;
-    const int warp_bytes = tall ? kWarpBytesTall : kWarpBytesShort;
-    uint8_t* ring = smem + ((kOffWarp + NW * warp_bytes + 127) & ~127);
-    const uint32_t map_bytes = static_cast<uint32_t>(R) * W;
+    const uint32_t srow = static_cast<uint32_t>(min(W, kStrip));          // bytes per staged strip row
+    const uint32_t map_bytes = static_cast<uint32_t>(R) * srow;
     const uint32_t stage_bytes = 2 * map_bytes;
+    const int state_bytes = kWarpBars + (tall ? kWarpBytesTall : kWarpBytesShort);
+    const int warp_bytes = state_bytes + S * static_cast<int>(stage_bytes);   // multiple of 128
 
     for (int i = tid; i < 256; i += blockDim.x) cta_counts[i] = 0;
     if (tid < 16) cta_sq[tid] = cta_abs[tid] = cta_thick[tid] = 0;
     if (tid < 32) cta_first[tid] = OCTM_NO_SEED;
-    for (int i = tid; i < NW * warp_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + kOffWarp)[i] = 0;
-    uint32_t* done_cnt = reinterpret_cast<uint32_t*>(empty);   // warps finished with the slot's current fill
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            done_cnt[s] = 0;
-        }
+    uint8_t* wbase = smem + kOffWarp + warp * warp_bytes;
+    for (int i = lane; i < state_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(wbase)[i] = 0;
+    const uint32_t bars = smem_u32(wbase);                                  // full[s] at bars + 8 s
+    const uint32_t ring_addr = bars + state_bytes;
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init_a(bars + 8 * s, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------------- ring fills
-    // There is no producer warp.  The CTA's stages form one fixed sequence (item by item, R rows at a
-    // time); fill f lives in slot f % S.  The LAST warp to finish a slot (shared-memory counter) issues
-    // fill f + S into it: two 1-D TMA bulk copies (one per map) completing on the slot's mbarrier.
-    // Every warp tracks the coordinates of fill f + S in registers (nf_item, nf_r0).
+    // ---------------------------------------------------------------------- ring fills (per warp)
+    // The warp's stages form one fixed sequence (item by item, R rows at a time); fill f lives in slot
+    // f % S and is issued by lane 0 right after fill f - S has been consumed.  A box always has R rows:
+    // past the end of an item it carries rows of the next one (never read), past the end of the tensor zeros.
     const uint64_t pol = policy_evict_first();
+    const int x0 = warp * kStrip;
     auto issue_fill = [&](long long it, int r0, uint32_t slot) {
-        const uint32_t bytes = static_cast<uint32_t>(min(R, H - r0)) * W;
-        const long long off = (it * H + r0) * static_cast<long long>(W);
-        uint8_t* dst = ring + static_cast<size_t>(slot) * stage_bytes;
-        mbar_arrive_expect_tx(&full[slot], 2 * bytes);
-        bulk_g2s(dst, prm.yt + off, bytes, &full[slot], pol);
-        bulk_g2s(dst + map_bytes, prm.yp + off, bytes, &full[slot], pol);
+        const uint32_t dst = ring_addr + slot * stage_bytes;
+        const int y = static_cast<int>(it * H + r0);
+        mbar_expect_tx_a(bars + 8 * slot, stage_bytes);
+        tma_load_2d(dst, &tm_true, x0, y, bars + 8 * slot, pol);
+        tma_load_2d(dst + map_bytes, &tm_pred, x0, y, bars + 8 * slot, pol);
     };
     long long nf_item = blockIdx.x;
     int nf_r0 = 0;
     for (int f = 0; f < S; ++f) {
-        if (tid == 0 && nf_item < prm.n_items) issue_fill(nf_item, nf_r0, f);
+        if (lane == 0 && nf_item < prm.n_items) issue_fill(nf_item, nf_r0, f);
         nf_r0 += R;
         if (nf_r0 >= H) { nf_r0 = 0; nf_item += gridDim.x; }
     }
 
     // ---------------------------------------------------------------------- consumers
-    uint8_t* wbase = smem + kOffWarp + warp * warp_bytes;
-    unsigned short* hist = reinterpret_cast<unsigned short*>(wbase);                         // [64][32]
+    unsigned short* hist = reinterpret_cast<unsigned short*>(wbase + kWarpBars);             // [64][32]
     unsigned short* hist_lane = hist + lane;
-    uint4* queue = reinterpret_cast<uint4*>(wbase + kWarpHist);
-    unsigned short* totals = tall ? reinterpret_cast<unsigned short*>(wbase + kWarpHist + kWarpQueue) : hist;   // [2][8][128]
+    uint4* queue = reinterpret_cast<uint4*>(wbase + kWarpBars + kWarpHist);
+    unsigned short* totals = tall ? reinterpret_cast<unsigned short*>(wbase + kWarpBars + kWarpHist + kWarpQueue) : hist;   // [2][8][128]
     const int phase = lane >> 4;
     const int col = warp * kStrip + (lane & 15) * 8;      // first of this lane's 8 columns
     const bool colv = col < W;
     const bool strip_full = (warp + 1) * kStrip <= W;      // warp-uniform
     const int nthr = K - 1;
     const int consumers = NW * 32;
-    const uint32_t lane_off = static_cast<uint32_t>(phase) * W + col;
-    const uint32_t ring_addr = smem_u32(ring);
+    const uint32_t lane_smem = static_cast<uint32_t>(phase) * srow + (lane & 15) * 8;     // inside a staged strip
+    const uint32_t lane_pos = static_cast<uint32_t>(phase) * W + col;                       // inside the image
 
     StageConsts sc;
-    sc.W2 = 2u * W; sc.W4 = 4u * W; sc.map_bytes = map_bytes; sc.one = prm.one;
+    sc.srow2 = 2u * srow; sc.srow4 = 4u * srow; sc.W2 = 2u * W; sc.W4 = 4u * W;
+    sc.map_bytes = map_bytes; sc.one = prm.one; sc.all_classes = ((1u << K) - 1u) * 0x101u;
     sc.phase = phase; sc.lane = lane; sc.colv = colv;
     sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.cta_first = cta_first;
     LaneState<NP> ls;
@@ -426,23 +437,17 @@ __global__ void __launch_bounds__(WIDE ? 16 * 32 : 8 * 32, WIDE ? 1 : 2) label_p
 
         for (int r0 = 0; r0 < H; r0 += R) {
             const int rows = min(R, H - r0);
-            mbar_wait(&full[s], ph);
-            const uint32_t at = ring_addr + s * stage_bytes + lane_off;      // this lane's first row, y_true
-            const uint32_t pos = static_cast<uint32_t>(r0) * W + lane_off;    // its raster index in the item
+            mbar_wait_parked_a(bars + 8 * s, ph);
+            const uint32_t at = ring_addr + s * stage_bytes + lane_smem;        // this lane's first row, y_true
+            const uint32_t pos = static_cast<uint32_t>(r0) * W + lane_pos;       // its raster index in the item
             if (strip_full && (rows & 3) == 0)       // warp-uniform: every lane has both of its rows
                 stage_rows<NP, CONF, COLS, SEEDS, true>(ls, at, pos, rows, sc);
             else                                     // ragged strip or last rows of the item
                 stage_rows<NP, CONF, COLS, SEEDS, false>(ls, at, pos, rows, sc);
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(&done_cnt[s], 1u) == static_cast<uint32_t>(NW - 1)) {
-                    // every warp is done with this slot: refill it (fence orders their reads before the copy)
-                    done_cnt[s] = 0;
-                    __threadfence_block();
-                    fence_proxy_async();
-                    if (nf_item < prm.n_items) issue_fill(nf_item, nf_r0, s);
-                }
+            __syncwarp();                            // every lane has read the slot
+            if (lane == 0 && nf_item < prm.n_items) {
+                fence_proxy_async();                 // generic reads of the slot before the async overwrite
+                issue_fill(nf_item, nf_r0, s);
             }
             nf_r0 += R;
             if (nf_r0 >= H) { nf_r0 = 0; nf_item += gridDim.x; }
@@ -692,28 +697,66 @@ static bool fast_ok(int H, int W, int K, const void* a, const void* b) {
            (reinterpret_cast<uintptr_t>(a) % 16 == 0) && (reinterpret_cast<uintptr_t>(b) % 16 == 0);
 }
 
+// cuTensorMapEncodeTiled, fetched through the runtime so that liboctm.so does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// label tensor [n_items * H rows][W columns] of uint8; one box = R rows x min(W, 128) columns, dense in smem
+static int make_label_map(CUtensorMap* tm, const uint8_t* base, long long rows, int W, int R) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (enc == nullptr) return fail(OCTM_ERR_LAUNCH, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(W)};            // bytes between rows
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(W < kStrip ? W : kStrip), static_cast<cuuint32_t>(R)};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), gdim, gstride, box, estride,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OCTM_ERR_LAUNCH, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    return OCTM_OK;
+}
+
 template <int NP, bool CONF, bool COLS, bool SEEDS>
 static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     LabelPassParams p = p0;
     p.one = 1;
     const int NW = (p.W + kStrip - 1) / kStrip;
-    // rows per stage: ~8 KB per map (multiple of 4 rows), 2 stages per CTA: with 4 resident CTAs per SM that
-    // is 8 fills in flight per SM, and occupancy (shared memory) matters more than ring depth here.
+    // each warp stages its own 128-column strip: R rows per stage (multiple of 4), S stages.  16 rows x 2 stages =
+    // 8 KB of ring per warp; shared memory (occupancy) matters more than ring depth here.
     // OCTM_LP_ROWS / OCTM_LP_STAGES override for tuning runs.
     static const int env_rows = [] { const char* e = getenv("OCTM_LP_ROWS"); return e ? atoi(e) : 0; }();
     static const int env_stages = [] { const char* e = getenv("OCTM_LP_STAGES"); return e ? atoi(e) : 0; }();
-    int R = (8192 / p.W) & ~3;
+    int R = 16;
     if (env_rows > 0) R = env_rows & ~3;
     if (R < 4) R = 4;
+    if (R > 256) R = 256;                                  // TMA box limit
     p.R = R;
-    const int fixed = ((kOffWarp + NW * (p.H > kShortRows ? kWarpBytesTall : kWarpBytesShort) + 127) & ~127);
-    const int stage = 2 * R * p.W;
+    const int srow = p.W < kStrip ? p.W : kStrip;
+    const int state = kWarpBars + (p.H > kShortRows ? kWarpBytesTall : kWarpBytesShort);
+    const int stage = 2 * R * srow;
     const int budget = max_optin_smem();
     int S = env_stages >= 2 && env_stages <= kMaxStages ? env_stages : 2;
-    while (S > 2 && fixed + S * stage > budget) --S;
+    while (S > 2 && kOffWarp + NW * (state + S * stage) > budget) --S;
     p.S = S;
-    const int smem = fixed + S * stage;
+    const int smem = kOffWarp + NW * (state + S * stage);
     if (smem > budget) return fail(OCTM_ERR_UNSUPPORTED, "label pass: %d B of shared memory needed", smem);
+    CUtensorMap tm_true, tm_pred;
+    const long long rows = p.n_items * p.H;
+    if (int e = make_label_map(&tm_true, p.yt, rows, p.W, R)) return e;
+    if (int e = make_label_map(&tm_pred, p.yp, rows, p.W, R)) return e;
     auto kern = NW > 8 ? label_pass_fast<NP, CONF, COLS, SEEDS, true> : label_pass_fast<NP, CONF, COLS, SEEDS, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess)
         return fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(label_pass_fast) failed");
@@ -725,7 +768,7 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     }
     long long grid = static_cast<long long>(sm_count()) * per_sm;
     if (grid > p.n_items) grid = p.n_items;
-    kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p);
+    kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, tm_true, tm_pred);
     return check_launch("label_pass_fast");
 }
 
@@ -751,7 +794,8 @@ static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
 
 int run_label_pass(const LabelPassParams& p, bool conf, bool cols, bool seeds, cudaStream_t stream) {
     if (p.n_items == 0) return OCTM_OK;
-    if (fast_ok(p.H, p.W, p.K, p.yt, p.yp) && (p.bnd_t == nullptr || reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0) &&
+    if (fast_ok(p.H, p.W, p.K, p.yt, p.yp) && p.n_items * p.H < (1ll << 31) /* TMA row coordinate */ &&
+        (p.bnd_t == nullptr || reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0) &&
         (p.bnd_p == nullptr || reinterpret_cast<uintptr_t>(p.bnd_p) % 16 == 0)) {
         if (conf && cols && seeds) return dispatch_np<true, true, true>(p, stream);
         if (conf && cols) return dispatch_np<true, true, false>(p, stream);

@@ -60,11 +60,12 @@ def test_fast_path_predicate(lib):
     assert so.octm_label_pass_path(496, 512, 8, 8, 0) == 0        # misaligned pointer
 
 
-def test_sass_uses_tma_bulk_copies(lib):
-    """The staged label pass must really be TMA: UBLKCP in the sm_100a SASS."""
+def test_sass_uses_tma_tile_copies(lib):
+    """The staged label pass must really be TMA: UTMALDG (2-D tensor-map tile loads) in the sm_100a SASS."""
     r = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in r.stdout or "SM100a" in r.stdout or "sm_100" in r.stdout
-    assert "UBLKCP" in r.stdout
+    assert "UTMALDG" in r.stdout
+    assert "LDG.E.NA.EFL2.256" in r.stdout or ".256" in r.stdout      # 256-bit streaming loads of the argmax front end
     assert "SYNCS" in r.stdout        # mbarrier arrive / try_wait
