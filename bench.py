@@ -218,8 +218,15 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.5)                      # let nvidia-smi finish initialising before anything is timed
-    for _ in range(args.warmup):
-        step().result()
+    prev = None
+    for _ in range(args.warmup):          # two evaluations in flight, like the timed loop: primes torch's allocator
+        cur = step()
+        if prev is not None:
+            prev.result()
+        prev = cur
+    if prev is not None:
+        prev.result()
+    prev = cur = None
     barrier()
     timers.clear()
     gc.collect()
