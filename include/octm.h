@@ -169,6 +169,24 @@ OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pt
                             double* sum_dist, uint32_t* d2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 3-D surface-distance metrics (BASELINE config 5; the reference's contour metrics are 2-D only, this is
+ * their build-defined 3-D counterpart): per class, distances between the SURFACES of the class regions of
+ * two label volumes [D0][D1][D2] by an exact separable squared Euclidean distance transform (Meijster).
+ *   surface(mask) = voxels of the mask with a 6-neighbour outside it (outside the volume = outside)
+ *   unit u = class * 2 + direction; direction 0: every surface voxel of y_pred -> nearest surface voxel of
+ *   y_true, direction 1 the other way.  Units [unit_begin, unit_end) are computed (multi-GPU: disjoint
+ *   ranges per rank), outputs of the others are left untouched:
+ *   n_pts    uint32 [K][2]     surface voxels of y_true ([c][0], written by direction 1) / y_pred ([c][1]) that
+ *                              have a finite distance; 0 when either surface is empty
+ *   max_sq   uint32 [K][2], p95_sq uint32 [K][2][2], sum_dist double [K][2]: as for octm_contour2d_u8, but on
+ *                              the unit lattice (distance = sqrt(D2), not sqrt(D2 / 4))
+ * Limits: D0, D1 <= 2048, D2 <= 65534, squared diagonal < 2^28. */
+OCTM_API size_t octm_surface3d_workspace_bytes(int D0, int D1, int D2);
+OCTM_API int octm_surface3d_u8(const uint8_t* y_true, const uint8_t* y_pred, int D0, int D1, int D2, int num_classes,
+                      int unit_begin, int unit_end, uint32_t* n_pts, uint32_t* max_sq, uint32_t* p95_sq,
+                      double* sum_dist, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Front end: model scores -> uint8 label map, argmax over the class dimension (what a user does between
  * a model's forward() and the metric functions; every model of the reference returns
  * (B, num_classes, H, W), e.g. SOTAS/Lesions_Segment/ReLayNet_2017.py:106-108).

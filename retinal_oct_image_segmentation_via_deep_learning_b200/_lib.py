@@ -48,6 +48,8 @@ SIGNATURES = {
     "octm_auc_u8": (_INT, [_P, _P, _INT, _I64, _I64, _c.c_double, _P, _P, _c.c_size_t, _P]),
     "octm_boundary_error_float": (_INT, [_P, _P, _INT, _I64, _INT, _I64, _P, _P, _P]),
     "octm_topology_violations_float": (_INT, [_P, _INT, _I64, _INT, _I64, _P, _P, _P]),
+    "octm_surface3d_workspace_bytes": (_c.c_size_t, [_INT, _INT, _INT]),
+    "octm_surface3d_u8": (_INT, [_P, _P, _INT, _INT, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
     "octm_totals_len": (_INT, [_INT]),
     "octm_derive_metrics": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P]),
 }

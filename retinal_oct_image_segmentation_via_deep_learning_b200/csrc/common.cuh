@@ -157,6 +157,37 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+// exclusive prefix SUM over the threads of a CTA (blockDim a multiple of 32, <= 1024) in thread order;
+// s_warp: 33 elements of shared memory; `total` receives the sum over all threads.  Three CTA barriers.
+template <class T>
+__device__ __forceinline__ T block_excl_scan_sum(T v, T* s_warp, T& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        T w = s_warp[lane];
+        T wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    const T res = s_warp[warp] + incl - v;
+    total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace octm

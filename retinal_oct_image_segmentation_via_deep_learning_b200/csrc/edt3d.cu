@@ -1,0 +1,318 @@
+// 3-D surface-distance metrics (BASELINE config 5): Hausdorff, HD95 and ASSD between the SURFACES of the
+// class-c regions of two label volumes, by an exact separable squared-Euclidean distance transform.
+//
+// The reference's contour metrics (Metrics/Contour_based_metrics.py:5-56) are 2-D only; this is their
+// 3-D counterpart with the customary definition (build-defined, SURVEY.md 8c item 4, oracle in
+// oracle/surface3d_oracle.py):
+//   surface(mask) = voxels of the mask with a 6-neighbour outside it (outside the volume counts as outside)
+//                 = mask & ~scipy.ndimage.binary_erosion(mask)
+//   direction 0: for every surface voxel of y_pred the squared distance to the nearest surface voxel of
+//   y_true (unit spacing); direction 1 the other way round.  Per direction: count, max D2, the two order
+//   statistics numpy's linear 95th percentile interpolates, sum of sqrt(D2) in float64 -- the same
+//   integers / sums the 2-D kernels return, so derive.contour_metrics finishes both.
+//
+// Volume [D0][D1][D2], C-contiguous (D2 fastest).  Per (class, direction) unit:
+//   pass 1 (along D2)  one thread per line: source-surface test from the labels (six neighbours), two
+//                      sweeps -> g = distance along the line to the nearest surface voxel (uint16).
+//   pass 2 (along D1)  one thread per line, adjacent threads = adjacent D2 (coalesced): Meijster lower
+//                      envelope over (x - j)^2 + g(j)^2, the two stacks in local memory -> h2 (uint32).
+//   pass 3 (along D0)  the same envelope over h2, evaluated only at the QUERY volume's surface voxels;
+//                      the exact D2 values go into a histogram (shared-memory bins for small values,
+//                      global atomics for the rest).
+//   select             one CTA scans the histogram: count, max, order statistics, sum of count*sqrt(D2)
+//                      in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace octm {
+
+constexpr uint16_t kInf16 = 0xffffu;
+constexpr uint32_t kInf32 = 0xffffffffu;
+constexpr int kMaxLine = 2048;           // longest D0 / D1 line (local-memory stacks of 2 x uint16 per element and thread)
+constexpr int kSmemBins = 8192;          // squared distances below this are counted in shared memory
+
+struct Edt3Params {
+    const uint8_t* src;      // volume whose class surface is the source set
+    const uint8_t* qry;      // volume whose class surface holds the query voxels
+    int D0, D1, D2, cls;
+    uint16_t* g;             // [D0][D1][D2]
+    uint32_t* h2;            // [D0][D1][D2]
+    uint32_t* hist;          // [nbins]
+    uint32_t nbins;
+};
+
+__device__ __forceinline__ bool surface_at(const uint8_t* L, int D0, int D1, int D2, int i0, int i1, int i2, int cls) {
+    const long long s1 = D2, s0 = static_cast<long long>(D1) * D2;
+    const uint8_t* p = L + i0 * s0 + i1 * s1 + i2;
+    if (*p != cls) return false;
+    return i2 == 0 || p[-1] != cls || i2 == D2 - 1 || p[1] != cls || i1 == 0 || p[-s1] != cls || i1 == D1 - 1 || p[s1] != cls ||
+           i0 == 0 || p[-s0] != cls || i0 == D0 - 1 || p[s0] != cls;
+}
+
+// ------------------------------------------------------------------------------------------ pass 1
+__global__ void __launch_bounds__(128) edt3_pass1_kernel(const Edt3Params prm) {
+    const long long lines = static_cast<long long>(prm.D0) * prm.D1;
+    const int D0 = prm.D0, D1 = prm.D1, D2 = prm.D2, cls = prm.cls;
+    for (long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; line < lines;
+         line += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i0 = static_cast<int>(line / D1), i1 = static_cast<int>(line % D1);
+        const long long s0 = static_cast<long long>(D1) * D2;
+        const uint8_t* c = prm.src + line * D2;
+        const uint8_t* up = i0 > 0 ? c - s0 : nullptr;
+        const uint8_t* dn = i0 < D0 - 1 ? c + s0 : nullptr;
+        const uint8_t* lf = i1 > 0 ? c - D2 : nullptr;
+        const uint8_t* rt = i1 < D1 - 1 ? c + D2 : nullptr;
+        const bool border = !up || !dn || !lf || !rt;       // a missing neighbour line makes every mask voxel surface
+        uint16_t* g = prm.g + line * D2;
+        uint32_t dist = kInf16;
+        int prev = -1, cur = c[0];
+        for (int i2 = 0; i2 < D2; ++i2) {
+            const int nxt = i2 + 1 < D2 ? c[i2 + 1] : -1;
+            bool surf = false;
+            if (cur == cls)
+                surf = border || prev != cls || nxt != cls || up[i2] != cls || dn[i2] != cls || lf[i2] != cls || rt[i2] != cls;
+            dist = surf ? 0u : (dist == kInf16 ? kInf16 : min(dist + 1u, 0xfffeu));
+            g[i2] = static_cast<uint16_t>(dist);
+            prev = cur;
+            cur = nxt;
+        }
+        dist = kInf16;
+        for (int i2 = D2 - 1; i2 >= 0; --i2) {
+            const uint32_t f = g[i2];
+            if (f == 0u) dist = 0u;
+            else if (dist != kInf16) {
+                dist = min(dist + 1u, 0xfffeu);
+                if (dist < f) g[i2] = static_cast<uint16_t>(dist);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ envelope
+// Lower envelope of the parabolas  x -> (x - j)^2 + w(j)  over the finite sites j of one line
+// (Meijster et al.).  s[k] = site of region k, t[k] = first x of region k.  Returns the top index q
+// (-1: the line has no finite site).
+template <class W>
+__device__ __forceinline__ int build_envelope(int n, W weight, uint16_t* s, uint16_t* t) {
+    int q = -1;
+    for (int u = 0; u < n; ++u) {
+        const long long wu = weight(u);
+        if (wu < 0) continue;                                   // infinite site
+        while (q >= 0) {
+            const long long x = t[q], i = s[q];
+            const long long fi = (x - i) * (x - i) + weight(static_cast<int>(i));
+            const long long fu = (x - u) * (x - u) + wu;
+            if (fi > fu) --q;
+            else break;
+        }
+        if (q < 0) {
+            q = 0;
+            s[0] = static_cast<uint16_t>(u);
+            t[0] = 0;
+        } else {
+            const long long i = s[q];
+            // first x at which u's parabola is strictly... Meijster: Sep(i, u) = (u^2 - i^2 + w(u) - w(i)) div (2 (u - i))
+            const long long num = static_cast<long long>(u) * u - i * i + wu - weight(static_cast<int>(i));
+            const long long den = 2 * (u - i);
+            long long sep = num >= 0 ? num / den : -((-num + den - 1) / den);       // floor division
+            const long long w = sep + 1;
+            if (w < n) {
+                ++q;
+                s[q] = static_cast<uint16_t>(u);
+                t[q] = static_cast<uint16_t>(w < 0 ? 0 : w);
+            }
+        }
+    }
+    return q;
+}
+
+// ------------------------------------------------------------------------------------------ pass 2
+__global__ void __launch_bounds__(128) edt3_pass2_kernel(const Edt3Params prm) {
+    const int D0 = prm.D0, D1 = prm.D1, D2 = prm.D2;
+    const long long lines = static_cast<long long>(D0) * D2;
+    uint16_t s[kMaxLine], t[kMaxLine];
+    for (long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; line < lines;
+         line += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i0 = static_cast<int>(line / D2), i2 = static_cast<int>(line % D2);
+        const uint16_t* g = prm.g + static_cast<long long>(i0) * D1 * D2 + i2;       // element j at g[j * D2]
+        uint32_t* h = prm.h2 + static_cast<long long>(i0) * D1 * D2 + i2;
+        auto weight = [&](int j) -> long long {
+            const uint32_t v = g[static_cast<long long>(j) * D2];
+            return v == kInf16 ? -1ll : static_cast<long long>(v) * v;
+        };
+        int q = build_envelope(D1, weight, s, t);
+        if (q < 0) {
+            for (int x = 0; x < D1; ++x) h[static_cast<long long>(x) * D2] = kInf32;
+            continue;
+        }
+        for (int x = D1 - 1; x >= 0; --x) {
+            const long long i = s[q];
+            h[static_cast<long long>(x) * D2] = static_cast<uint32_t>((x - i) * (x - i) + weight(static_cast<int>(i)));
+            if (x == t[q]) --q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ pass 3
+__global__ void __launch_bounds__(128) edt3_pass3_kernel(const Edt3Params prm) {
+    __shared__ uint32_t s_hist[kSmemBins];
+    const int D0 = prm.D0, D1 = prm.D1, D2 = prm.D2, cls = prm.cls;
+    const long long plane = static_cast<long long>(D1) * D2;
+    for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    uint16_t s[kMaxLine], t[kMaxLine];
+    for (long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; line < plane;
+         line += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i1 = static_cast<int>(line / D2), i2 = static_cast<int>(line % D2);
+        const uint32_t* h = prm.h2 + line;                                          // element j at h[j * plane]
+        auto weight = [&](int j) -> long long {
+            const uint32_t v = h[static_cast<long long>(j) * plane];
+            return v == kInf32 ? -1ll : static_cast<long long>(v);
+        };
+        int q = build_envelope(D0, weight, s, t);
+        if (q < 0) continue;                                                        // no source surface at all
+        for (int x = D0 - 1; x >= 0; --x) {
+            if (surface_at(prm.qry, D0, D1, D2, x, i1, i2, cls)) {
+                const long long i = s[q];
+                const uint32_t d2 = static_cast<uint32_t>((x - i) * (x - i) + weight(static_cast<int>(i)));
+                if (d2 < static_cast<uint32_t>(kSmemBins)) atomicAdd(&s_hist[d2], 1u);
+                else atomicAdd(&prm.hist[min(d2, prm.nbins - 1)], 1u);
+            }
+            if (x == t[q]) --q;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c && static_cast<uint32_t>(i) < prm.nbins) atomicAdd(&prm.hist[i], c);
+    }
+}
+
+// query-surface count when the source surface is empty is not needed: the metrics are undefined then.
+// ------------------------------------------------------------------------------------------ select
+struct Sel3Params {
+    const uint32_t* hist;
+    uint32_t nbins;
+    uint32_t* n_pts;      // [1]
+    uint32_t* max_sq;     // [1]
+    uint32_t* p95_sq;     // [2]
+    double* sum_dist;     // [1]
+};
+
+__global__ void __launch_bounds__(1024) edt3_select_kernel(const Sel3Params prm) {
+    __shared__ unsigned long long s_scan[33];
+    __shared__ double s_dsum[32];
+    __shared__ uint32_t s_max[32];
+    __shared__ uint32_t s_sel[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = prm.nbins;
+    const uint32_t chunk = (n + 1023u) / 1024u;
+    const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
+    unsigned long long cnt = 0;
+    uint32_t vmax = 0;
+    double ds = 0.0;
+    for (uint32_t v = b; v < e; ++v) {
+        const uint32_t c = prm.hist[v];
+        if (c) {
+            cnt += c;
+            vmax = v;
+            ds = __dadd_rn(ds, __dmul_rn(static_cast<double>(c), sqrt(static_cast<double>(v))));
+        }
+    }
+    unsigned long long total;
+    const unsigned long long before = block_excl_scan_sum<unsigned long long>(cnt, s_scan, total);
+    // fixed-order float64 sum: lanes tree, then warps in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ds = __dadd_rn(ds, __shfl_xor_sync(0xffffffffu, ds, o));
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane == 0) { s_dsum[warp] = ds; s_max[warp] = vmax; }
+    if (tid < 2) s_sel[tid] = 0;
+    __syncthreads();
+    if (total > 0) {
+        // numpy linear percentile: virtual index (m - 1) * 0.95, neighbours floor and floor + 1
+        const double pos = __dmul_rn(static_cast<double>(total - 1), 0.95);
+        const unsigned long long k_lo = static_cast<unsigned long long>(floor(pos));
+        const unsigned long long k_hi = k_lo + 1 < total ? k_lo + 1 : k_lo;
+        unsigned long long run = before;
+        for (uint32_t v = b; v < e; ++v) {
+            const uint32_t c = prm.hist[v];
+            if (c) {
+                if (run <= k_lo && k_lo < run + c) s_sel[0] = v;
+                if (run <= k_hi && k_hi < run + c) s_sel[1] = v;
+                run += c;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        uint32_t m = 0;
+        for (int w = 0; w < 32; ++w) { sum = __dadd_rn(sum, s_dsum[w]); m = max(m, s_max[w]); }
+        prm.n_pts[0] = static_cast<uint32_t>(total > 0xffffffffull ? 0xffffffffull : total);
+        prm.max_sq[0] = m;
+        prm.p95_sq[0] = s_sel[0];
+        prm.p95_sq[1] = s_sel[1];
+        prm.sum_dist[0] = sum;
+    }
+}
+
+}  // namespace octm
+
+static uint32_t edt3_nbins(int D0, int D1, int D2) {
+    const unsigned long long m = 1ull * (D0 - 1) * (D0 - 1) + 1ull * (D1 - 1) * (D1 - 1) + 1ull * (D2 - 1) * (D2 - 1) + 1ull;
+    return static_cast<uint32_t>(m);
+}
+
+extern "C" size_t octm_surface3d_workspace_bytes(int D0, int D1, int D2) {
+    if (D0 < 1 || D1 < 1 || D2 < 1) return 0;
+    const size_t vox = static_cast<size_t>(D0) * D1 * D2;
+    auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+    return up(vox * 2) + up(vox * 4) + up(static_cast<size_t>(edt3_nbins(D0, D1, D2)) * 4);
+}
+
+extern "C" int octm_surface3d_u8(const uint8_t* y_true, const uint8_t* y_pred, int D0, int D1, int D2, int num_classes,
+                                 int unit_begin, int unit_end, uint32_t* n_pts, uint32_t* max_sq, uint32_t* p95_sq,
+                                 double* sum_dist, void* workspace, size_t workspace_bytes, void* stream) {
+    if (D0 < 1 || D1 < 1 || D2 < 1) return octm::fail(OCTM_ERR_INVALID, "bad volume shape");
+    if (num_classes < 1 || num_classes > 256) return octm::fail(OCTM_ERR_INVALID, "num_classes outside [1, 256]");
+    if (unit_begin < 0 || unit_end > 2 * num_classes || unit_begin > unit_end) return octm::fail(OCTM_ERR_INVALID, "bad unit range");
+    if (D0 > octm::kMaxLine || D1 > octm::kMaxLine || D2 > 65534)
+        return octm::fail(OCTM_ERR_UNSUPPORTED, "volume sides: D0, D1 <= %d and D2 <= 65534", octm::kMaxLine);
+    const unsigned long long far2 = 1ull * (D0 - 1) * (D0 - 1) + 1ull * (D1 - 1) * (D1 - 1) + 1ull * (D2 - 1) * (D2 - 1);
+    if (far2 >= (1ull << 28)) return octm::fail(OCTM_ERR_UNSUPPORTED, "squared diagonal %llu needs a histogram of more than 2^28 bins", far2);
+    if (!y_true || !y_pred || !n_pts || !max_sq || !p95_sq || !sum_dist) return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    if (workspace == nullptr || workspace_bytes < octm_surface3d_workspace_bytes(D0, D1, D2))
+        return octm::fail(OCTM_ERR_WORKSPACE, "workspace too small: need %zu B", octm_surface3d_workspace_bytes(D0, D1, D2));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t vox = static_cast<size_t>(D0) * D1 * D2;
+    auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint16_t* g = reinterpret_cast<uint16_t*>(ws);
+    uint32_t* h2 = reinterpret_cast<uint32_t*>(ws + up(vox * 2));
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + up(vox * 2) + up(vox * 4));
+    const uint32_t nbins = edt3_nbins(D0, D1, D2);
+    const int sms = octm::sm_count();
+    // the Meijster kernels keep 2 x kMaxLine uint16 of stack per thread in local memory
+    for (int unit = unit_begin; unit < unit_end; ++unit) {
+        const int cls = unit >> 1, dir = unit & 1;
+        // direction 0: queries = y_pred surface, sources = y_true surface (d1 of the reference); 1 swapped
+        octm::Edt3Params p{dir == 0 ? y_true : y_pred, dir == 0 ? y_pred : y_true, D0, D1, D2, cls, g, h2, hist, nbins};
+        if (cudaMemsetAsync(hist, 0, static_cast<size_t>(nbins) * 4, st) != cudaSuccess)
+            return octm::fail(OCTM_ERR_LAUNCH, "memset(hist) failed");
+        auto blocks = [&](long long threads) {
+            long long b = (threads + 127) / 128;
+            const long long cap = static_cast<long long>(sms) * 16;
+            return static_cast<unsigned>(b < cap ? b : cap);
+        };
+        octm::edt3_pass1_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
+        if (int e = octm::check_launch("edt3_pass1_kernel")) return e;
+        octm::edt3_pass2_kernel<<<blocks(1ll * D0 * D2), 128, 0, st>>>(p);
+        if (int e = octm::check_launch("edt3_pass2_kernel")) return e;
+        octm::edt3_pass3_kernel<<<blocks(1ll * D1 * D2), 128, 0, st>>>(p);
+        if (int e = octm::check_launch("edt3_pass3_kernel")) return e;
+        // n_pts keeps the 2-D layout [K][2] = (surface voxels of y_true, of y_pred): direction 0 queries y_pred's
+        octm::Sel3Params sp{hist, nbins, n_pts + cls * 2 + (1 - dir), max_sq + unit, p95_sq + 2 * unit, sum_dist + unit};
+        octm::edt3_select_kernel<<<1, 1024, 0, st>>>(sp);
+        if (int e = octm::check_launch("edt3_select_kernel")) return e;
+    }
+    return OCTM_OK;
+}

@@ -77,24 +77,26 @@ def _lerp(a, b, t):
     return np.where(t >= 0.5, alt, out)
 
 
-def contour_metrics(n_pts, max_sq, p95_sq, sum_dist):
+def contour_metrics(n_pts, max_sq, p95_sq, sum_dist, lattice=4.0):
     """hausdorff / hd95 / assd from the contour kernel's integers (Contour_based_metrics.py:22, 39, 56).
 
     ``n_pts [..., 2]`` (true, pred); ``max_sq [..., 2]``, ``p95_sq [..., 2, 2]``, ``sum_dist [..., 2]``
     indexed by direction (0: pred vertices -> true contour = ``d1``; 1: true -> pred = ``d2``).
-    Entries whose masks have no contour (the reference raises IndexError) come back as NaN."""
+    Entries whose masks have no contour (the reference raises IndexError) come back as NaN.
+    ``lattice``: squared length unit of the integer distances -- 4.0 for the doubled lattice of the 2-D
+    contours (distance = sqrt(D2 / 4)), 1.0 for the voxel lattice of the 3-D surfaces."""
     n_pts = np.asarray(n_pts).astype(np.int64)
     max_sq = np.asarray(max_sq).astype(np.int64)
     p95 = np.asarray(p95_sq).astype(np.float64)
     valid = (n_pts[..., 0] > 0) & (n_pts[..., 1] > 0)
     m = np.stack([n_pts[..., 1], n_pts[..., 0]], axis=-1)         # query count per direction
     msafe = np.maximum(m, 1)
-    hd = np.sqrt(np.maximum(max_sq[..., 0], max_sq[..., 1]).astype(np.float64) / 4.0)
+    hd = np.sqrt(np.maximum(max_sq[..., 0], max_sq[..., 1]).astype(np.float64) / lattice)
     # numpy percentile, method "linear": virtual index (m - 1) * 0.95
     pos = (msafe - 1) * (95 / 100)
     gamma = pos - np.floor(pos)
-    lo = np.sqrt(p95[..., 0] / 4.0)
-    hi = np.sqrt(p95[..., 1] / 4.0)
+    lo = np.sqrt(p95[..., 0] / lattice)
+    hi = np.sqrt(p95[..., 1] / lattice)
     pct = _lerp(lo, hi, gamma)
     hd95 = np.maximum(pct[..., 0], pct[..., 1])
     mean = np.asarray(sum_dist, dtype=np.float64) / msafe

@@ -170,3 +170,30 @@ def layered_pair_device(n, h, w, num_classes, seed, device, jitter=1.5, noise=0.
             rnd = torch.randint(0, num_classes, (m, h, w), generator=g, device=device, dtype=torch.uint8)
             y_pred[s:s + m] = torch.where(salt, rnd, y_pred[s:s + m])
     return y_true, y_pred
+
+
+def layered_volume_pair(d0, d1, d2, num_classes, seed, jitter=1.0):
+    """(vol_true, vol_pred) ``uint8 [d0, d1, d2]`` label volumes with depth along axis 0: K-1 smooth
+    surfaces ``b_k(x, z)`` stacked top to bottom; the prediction shifts and jitters every surface
+    (BASELINE config 5: ``1024 x 1024 x 128``, 11 classes)."""
+    rng = np.random.default_rng(seed)
+    nb = num_classes - 1
+    x = np.arange(d1, dtype=np.float64)[None, :, None]
+    z = np.arange(d2, dtype=np.float64)[None, None, :]
+    base = d0 * (0.15 + 0.7 * (np.arange(nb, dtype=np.float64) + 0.5) / nb)[:, None, None]
+    wave = 0.04 * d0 * np.sin(2 * np.pi * x / rng.uniform(0.7 * d1, 2.0 * d1) + rng.uniform(0, 6.28)) * \
+        np.cos(2 * np.pi * z / rng.uniform(1.0 * d2, 3.0 * d2) + rng.uniform(0, 6.28))
+    bt = np.sort(base + wave, axis=0)
+    gap = np.arange(nb, dtype=np.float64)[:, None, None] * 2
+    bt = np.clip(np.maximum.accumulate(bt - gap, axis=0) + gap, 1, d0 - 1)
+    bp = bt + rng.uniform(-1.5, 1.5, size=(nb, 1, 1)) + rng.normal(0.0, jitter, size=bt.shape)
+    bp = np.clip(np.maximum.accumulate(np.sort(bp, axis=0) - gap, axis=0) + gap, 1, d0 - 1)
+    y = np.arange(d0, dtype=np.int32)[:, None, None]
+
+    def raster(b):
+        vol = np.zeros((d0, d1, d2), dtype=np.uint8)
+        bi = np.rint(b).astype(np.int32)
+        for k in range(nb):
+            vol += (bi[k][None] <= y).astype(np.uint8)
+        return vol
+    return raster(bt), raster(bp)
