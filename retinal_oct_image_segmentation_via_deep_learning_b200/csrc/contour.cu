@@ -41,7 +41,35 @@ struct TraceParams {
     uint32_t* flags;             // [n][K]
 };
 
-__global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
+// 16 aligned label bytes from global memory unless the lane already holds them (`w` keeps its value when
+// tag == widx).  A predicated load, not a branch: lanes of a warp hit and miss independently.  On a miss the
+// same columns of the two rows above and below are prefetched into L2: the walk is latency-bound on exactly
+// these first touches (ncu: 72 % of its stall samples wait on the label loads, which miss L2).
+__device__ __forceinline__ void load_row16_if_new(uint4& w, uint32_t tag, uint32_t widx, const uint4* base, const uint4* up1,
+                                                  const uint4* dn1, const uint4* up2, const uint4* dn2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %4, %5;\n"
+        "@p ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%6];\n"
+#ifdef OCTM_TRACE_PREFETCH
+        "@p prefetch.global.L2 [%7];\n"
+        "@p prefetch.global.L2 [%8];\n"
+        "@p prefetch.global.L2 [%9];\n"
+        "@p prefetch.global.L2 [%10];\n"
+#endif
+        "}\n"
+        : "+r"(w.x), "+r"(w.y), "+r"(w.z), "+r"(w.w)
+        : "r"(tag), "r"(widx), "l"(base), "l"(up1), "l"(dn1), "l"(up2), "l"(dn2));
+}
+
+// WORDS: W % 16 == 0 and 16-byte aligned maps -> the walk reads aligned 16-byte label groups and keeps the last
+// group of the even and of the odd row in registers.
+#ifndef OCTM_TRACE_MINB
+#define OCTM_TRACE_MINB 8
+#endif
+template <bool WORDS>
+__global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const TraceParams prm) {
     __shared__ uint32_t s_step[64];      // step_word table: (case, entry edge) -> exit edge, vertex offset, order
     if (threadIdx.x < 64) s_step[threadIdx.x] = step_word(threadIdx.x);
     __syncthreads();
@@ -80,6 +108,11 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
     if (seed != OCTM_NO_SEED) {
         const uint32_t cap = static_cast<uint32_t>(prm.max_pts);
         uint32_t g0 = 0, g1 = 0, g2 = 0;
+        // register cache of the last aligned 16-byte label group of an even (0) and an odd (1) row
+        const uint4* L16 = reinterpret_cast<const uint4*>(L);
+        const uint32_t w16 = static_cast<uint32_t>(W) >> 4, hmax = static_cast<uint32_t>(H - 1);
+        uint32_t tag0 = 0xffffffffu, tag1 = 0xffffffffu;
+        uint4 row0 = make_uint4(0, 0, 0, 0), row1 = row0;
         const uint32_t c4 = 0x01010101u * static_cast<uint32_t>(cls);
         const TraceResult r = trace_first_contour(
             H, W, seed,
@@ -92,6 +125,29 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceParams prm) {
             },
             [&](int r0, int c0, int e) -> int {
                 // the two pixels not shared with the previous square (trace_core.h: carried_bits)
+                if (WORDS) {
+                    const uint32_t ra = r0 + (e == 1), ca = c0 + (e == 3);
+                    const uint32_t rb = ra + (e >= 2), cb = ca + (e < 2);
+                    int bits = 0;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t r = k ? rb : ra, c = k ? cb : ca;
+                        const uint32_t widx = r * w16 + (c >> 4);
+                        const bool odd = r & 1u;
+                        uint4 w = odd ? row1 : row0;
+                        const uint32_t rm1 = r > 0 ? r - 1 : 0, rm2 = r > 1 ? r - 2 : 0;
+                        const uint32_t rp1 = min(r + 1, hmax), rp2 = min(r + 2, hmax);
+                        const uint4* col = L16 + (c >> 4);
+                        load_row16_if_new(w, odd ? tag1 : tag0, widx, L16 + widx, col + rm1 * w16, col + rp1 * w16,
+                                          col + rm2 * w16, col + rp2 * w16);
+                        tag0 = odd ? tag0 : widx; tag1 = odd ? widx : tag1;
+                        if (odd) row1 = w; else row0 = w;
+                        const uint32_t q = (c >> 2) & 3u;
+                        const uint32_t word = q < 2 ? (q == 0 ? w.x : w.y) : (q == 2 ? w.z : w.w);
+                        bits |= (((word >> ((c & 3u) * 8u)) & 0xffu) == static_cast<uint32_t>(cls) ? 1 : 0) << k;
+                    }
+                    return bits;
+                }
                 const uint8_t* p = L + (static_cast<uint32_t>(r0) * static_cast<uint32_t>(W) + static_cast<uint32_t>(c0));
                 const int oa = (e == 1 ? W : 0) + (e == 3 ? 1 : 0), ob = oa + ((e & 2) ? W : 1);
                 return (__ldg(p + oa) == cls ? 1 : 0) | (__ldg(p + ob) == cls ? 2 : 0);
@@ -741,11 +797,20 @@ extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_p
     octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags};
     const long long threads = n_items * num_classes * 2;
     static const int env_ctas = [] { const char* e = getenv("OCTM_TRACE_CTAS"); return e ? atoi(e) : 0; }();
-    const int ctas_per_sm = env_ctas > 0 ? env_ctas : 6;
+    const bool words_probe = W % 16 == 0;
+    int fit = 0;       // persistent grid: every CTA that can be resident (the walk is latency-bound: occupancy hides it)
+    if ((words_probe ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<true>, 128, 0)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<false>, 128, 0)) != cudaSuccess || fit < 1) {
+        cudaGetLastError();
+        fit = 8;
+    }
+    const int ctas_per_sm = env_ctas > 0 ? env_ctas : fit;
     long long grid = (threads + 127) / 128;
     const long long cap = static_cast<long long>(octm::sm_count()) * ctas_per_sm;
     if (grid > cap) grid = cap;
-    octm::trace_kernel<<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
+    const bool words = W % 16 == 0 && reinterpret_cast<uintptr_t>(y_true) % 16 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 16 == 0;
+    if (words) octm::trace_kernel<true><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
+    else octm::trace_kernel<false><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
     return octm::check_launch("trace_kernel");
 }
 
