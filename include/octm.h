@@ -213,6 +213,15 @@ OCTM_API int octm_auc_u8(const uint8_t* y_true, const void* scores, int dtype, i
                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Transfer encoding for host-resident label maps (K <= 16): two labels per byte across PCIe.
+ *   octm_host_pack_nibbles   HOST function: dst[i] = src[2i] | src[2i+1] << 4 for n_labels labels
+ *                            (dst holds (n_labels + 1) / 2 bytes), on `threads` host threads (<= 0: all cores).
+ *                            A data-format conversion only; no metric arithmetic runs on the host.
+ *   octm_unpack_nibbles_u8   device kernel: the inverse, packed (device) -> labels uint8 [n_labels] (device). */
+OCTM_API int octm_host_pack_nibbles(const uint8_t* src, uint8_t* dst, size_t n_labels, int threads);
+OCTM_API int octm_unpack_nibbles_u8(const uint8_t* packed, int64_t n_labels, uint8_t* labels, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Float64 epilogue on the device.  class_metrics[i][c][m] (double [n][K][OCTM_NUM_CLASS_METRICS]) holds
  * the value the reference function OCTM_M_* returns for the masks (y_true == c, y_pred == c) of
  * item i, evaluated from the exact integers above with the reference's operation order

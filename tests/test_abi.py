@@ -69,3 +69,19 @@ def test_sass_uses_tma_tile_copies(lib):
     assert "UTMALDG" in r.stdout
     assert "LDG.E.NA.EFL2.256" in r.stdout or ".256" in r.stdout      # 256-bit streaming loads of the argmax front end
     assert "SYNCS" in r.stdout        # mbarrier arrive / try_wait
+
+
+def test_host_nibble_packer(lib):
+    """octm_host_pack_nibbles is a host function (transfer encoding): exercised here without a GPU."""
+    import numpy as np
+    so = lib.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 63, 64, 65, 100003, 1 << 21):
+        src = rng.integers(0, 16, n, dtype=np.uint8)
+        dst = np.full((n + 1) // 2 + 8, 0xAA, np.uint8)
+        assert so.octm_host_pack_nibbles(src.ctypes.data, dst.ctypes.data, n, 3) == 0
+        ref = np.zeros((n + 1) // 2, np.uint8)
+        ref[:n // 2] = src[0:n - (n & 1):2] | (src[1::2] << 4)
+        if n & 1:
+            ref[-1] = src[-1]
+        assert np.array_equal(dst[:(n + 1) // 2], ref) and (dst[(n + 1) // 2:] == 0xAA).all()

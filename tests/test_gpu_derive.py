@@ -70,6 +70,27 @@ def test_evaluate_host_streams_chunks(cuda):
     k = 5
     yt, yp = synth.layered_pair(11, 48, 64, k, seed=65, noise=0.02)
     a = suite.evaluate(torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda), k).metrics()
-    b = suite.evaluate_host(yt, yp, k, device=cuda, chunk_items=4).metrics()
-    for name in a:
-        assert _same(a[name], b[name]), name
+    for pack in (True, False, "auto"):           # packed transfer (two labels per byte) and the plain copy agree
+        b = suite.evaluate_host(yt, yp, k, device=cuda, chunk_items=4, pack=pack).metrics()
+        for name in a:
+            assert _same(a[name], b[name]), (name, pack)
+
+
+def test_packed_transfer_odd_sizes(cuda):
+    """host pack -> device unpack round trip on sizes that are not multiples of the vector widths"""
+    import ctypes
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(66)
+    for n in (1, 2, 31, 32, 33, 4097, 1 << 20, (1 << 20) + 17):
+        src = rng.integers(0, 16, n, dtype=np.uint8)
+        packed = np.zeros((n + 1) // 2, np.uint8)
+        assert lib.octm_host_pack_nibbles(src.ctypes.data, packed.ctypes.data, n, 4) == 0
+        dp = torch.from_numpy(packed).to(cuda)
+        out = torch.full((n + 5,), 0xEE, dtype=torch.uint8, device=cuda)
+        _lib.call("octm_unpack_nibbles_u8", ctypes.c_void_p(dp.data_ptr()), n, ctypes.c_void_p(out.data_ptr()),
+                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        got = out.cpu().numpy()
+        np.testing.assert_array_equal(got[:n], src)
+        assert (got[n:] == 0xEE).all()
