@@ -255,13 +255,15 @@ template <int NP>
 struct LaneState {
     ColState<NP> cs;
     uint32_t qhead, qtail;
-    uint32_t last_b;      // joint code (byte-replicated) of this lane's last uniform row pair
+    uint32_t last_b;      // joint code (byte-replicated) of this lane's current run of uniform row pairs
+    uint32_t run;         // pixel pairs of that run not yet in the histogram
     uint32_t warp_seen;   // classes this warp has met in this item (presence_bits layout, warp-uniform)
     int nib_fill, byt_fill;
     __device__ __forceinline__ void reset(bool cols) {
         if (cols) cs.clear();
         qhead = qtail = 0;
         last_b = 0xffffffffu;
+        run = 0;
         warp_seen = 0;
         nib_fill = byt_fill = 0;
     }
@@ -311,11 +313,17 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
             const uint32_t b = prmt(j.x, 0, 0);
             // uniform lane: all 16 pixel pairs share one joint code (padded lanes never take this path)
             const bool uni = FULL && (((j.x ^ b) | (j.y ^ b)) | ((j.z ^ b) | (j.w ^ b))) == 0;
-            if (CONF && uni) hist_add(sc.hist_lane, b & 0x3fu, 16);
-            const bool changed = SEEDS && uni && b != ls.last_b;
-            if (SEEDS && uni) ls.last_b = b;
+            // uniform row pairs come in long runs of one joint code (a lane stays inside a layer for many rows): the
+            // run length lives in a register and reaches the lane's private histogram column when the code changes
+            const bool changed = uni && b != ls.last_b;
+            if (uni && !changed) ls.run += 16u;
             const bool mixed_lane = FULL ? !uni : (va || vb);
             if (__any_sync(0xffffffffu, mixed_lane || changed)) {
+                if (changed) {
+                    if (CONF && ls.last_b != 0xffffffffu) hist_add(sc.hist_lane, ls.last_b & 0x3fu, ls.run);
+                    ls.last_b = b;
+                    ls.run = 16u;
+                }
                 if (SEEDS) {
                     // classes are tracked per WARP: rows only grow from pass to pass, so once any lane has
                     // met a class, later passes cannot hold an earlier pixel of it
@@ -459,6 +467,7 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
         // 504 rows (no mid-item byte flush) the column totals reuse that block.
         if (CONF) {
             // leftover queue entries, then fold the 32 private histogram columns
+            if (ls.last_b != 0xffffffffu) hist_add(hist_lane, ls.last_b & 0x3fu, ls.run);      // the open run
             const uint32_t left = ls.qtail - ls.qhead;
             __syncwarp();
             if (static_cast<uint32_t>(lane) < left) drain_entry(hist_lane, queue[(ls.qhead + lane) & (kQueueCap - 1)]);
@@ -577,10 +586,14 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
 }
 
 // ------------------------------------------------------------------------------------ generic
-// Any H, W and K <= 16.  One CTA per item (grid-stride); thread = column (stride blockDim).
-template <int NT>   // number of thresholds tracked in registers (K - 1 <= NT)
+// Any H, W and K <= 16 (the fast kernel takes K <= 8, W % 16 == 0).  One CTA per item (grid-stride); a thread
+// walks one column at a time (stride blockDim), so adjacent threads read adjacent bytes of a row.  Down a column
+// the joint code (t, p) comes in long RUNS (a column stays inside a layer for many rows): only a run's length
+// is accumulated per pixel; when the code changes the run goes into the warp's shared-memory confusion
+// histogram (one atomic per run, not per pixel) and into the thread's own per-class column counters.
 __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams prm) {
-    __shared__ uint32_t s_counts[8][256];
+    __shared__ uint32_t s_counts[8][256];                 // per-warp confusion histogram, code = t * 16 + p
+    __shared__ unsigned short s_cls[2][16][256];          // per-thread class counts of the current column
     __shared__ unsigned long long s_sq[16], s_abs[16], s_thick[16];
     __shared__ uint32_t s_first[2][16];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -592,49 +605,86 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
         __syncthreads();
         const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
         const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
+        // this thread's sums over its columns in 32 bits; squares go straight to the 64-bit shared sums when
+        // H^2 x (columns per thread) could overflow them
+        const bool wide = static_cast<unsigned long long>(H) * H * ((W + 255) / 256) >= (1ull << 32);
+        uint32_t acc_sq[15], acc_abs[15], acc_th[16];
+#pragma unroll
+        for (int j = 0; j < 15; ++j) acc_sq[j] = acc_abs[j] = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc_th[j] = 0;
         for (int x = tid; x < W; x += 256) {
-            uint32_t seen_t = 0, seen_p = 0;   // raster index grows with y inside one column
-            int ct[NT], cp[NT];
 #pragma unroll
-            for (int j = 0; j < NT; ++j) ct[j] = cp[j] = 0;
+            for (int c = 0; c < 16; ++c) s_cls[0][c][tid] = s_cls[1][c][tid] = 0;
+            uint32_t seen_t = 0, seen_p = 0;     // raster index grows with y inside one column
+            uint32_t run_code = 0xffffffffu, run = 0;
+            auto flush = [&]() {
+                if (run) {
+                    const uint32_t t = run_code >> 4, p = run_code & 15u;
+                    atomicAdd(&s_counts[warp][run_code], run);
+                    s_cls[0][t][tid] = static_cast<unsigned short>(s_cls[0][t][tid] + run);
+                    s_cls[1][p][tid] = static_cast<unsigned short>(s_cls[1][p][tid] + run);
+                }
+            };
+#pragma unroll 4
             for (int y = 0; y < H; ++y) {
-                const uint32_t t = bt[static_cast<long long>(y) * W + x], p = bp[static_cast<long long>(y) * W + x];
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    ct[j] += (t > static_cast<uint32_t>(j)) ? 1 : 0;
-                    cp[j] += (p > static_cast<uint32_t>(j)) ? 1 : 0;
+                const uint32_t t = bt[static_cast<long long>(y) * W + x] & 15u, p = bp[static_cast<long long>(y) * W + x] & 15u;
+                const uint32_t code = t * 16u + p;
+                if (code != run_code) {
+                    flush();
+                    run_code = code;
+                    run = 0;
+                    if (!((seen_t >> t) & 1u)) {
+                        seen_t |= 1u << t;
+                        atomicMin(&s_first[0][t], static_cast<uint32_t>(y * W + x));
+                    }
+                    if (!((seen_p >> p) & 1u)) {
+                        seen_p |= 1u << p;
+                        atomicMin(&s_first[1][p], static_cast<uint32_t>(y * W + x));
+                    }
                 }
-                atomicAdd(&s_counts[warp][(t & 15) * 16 + (p & 15)], 1u);
-                if (!((seen_t >> (t & 31)) & 1)) {
-                    seen_t |= 1u << (t & 31);
-                    atomicMin(&s_first[0][t & 15], static_cast<uint32_t>(y * W + x));
-                }
-                if (!((seen_p >> (p & 31)) & 1)) {
-                    seen_p |= 1u << (p & 31);
-                    atomicMin(&s_first[1][p & 15], static_cast<uint32_t>(y * W + x));
-                }
+                ++run;
             }
-            // column arithmetic: ct[j] = #{label >= j+1}
-            int prev_t = H, prev_p = H;
+            flush();
+            // column arithmetic from the class counts: #{label >= k} by a suffix sum over the classes
+            int ge_t = 0, ge_p = 0;
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                if (j < nthr) {
-                    const long long d = ct[j] - cp[j];
-                    atomicAdd(&s_sq[j], static_cast<unsigned long long>(d * d));
-                    atomicAdd(&s_abs[j], static_cast<unsigned long long>(d < 0 ? -d : d));
-                    const int dt = (prev_t - ct[j]) - (prev_p - cp[j]);
-                    atomicAdd(&s_thick[j], static_cast<unsigned long long>(dt < 0 ? -dt : dt));
-                    prev_t = ct[j];
-                    prev_p = cp[j];
+            for (int c = 15; c >= 0; --c) {
+                const int ct = s_cls[0][c][tid], cp = s_cls[1][c][tid];
+                if (c < K) acc_th[c] += static_cast<uint32_t>(abs(ct - cp));
+                ge_t += ct;
+                ge_p += cp;
+                if (c >= 1 && c <= nthr) {                                  // threshold k = c
+                    const int d = ge_t - ge_p;
+                    if (wide) atomicAdd(&s_sq[c - 1], static_cast<unsigned long long>(static_cast<long long>(d) * d));
+                    else acc_sq[c - 1] += static_cast<uint32_t>(d * d);
+                    acc_abs[c - 1] += static_cast<uint32_t>(abs(d));
                     if (prm.bnd_t != nullptr) {
-                        prm.bnd_t[(item * nthr + j) * W + x] = H - ct[j];
-                        prm.bnd_p[(item * nthr + j) * W + x] = H - cp[j];
+                        prm.bnd_t[(item * nthr + (c - 1)) * W + x] = H - ge_t;
+                        prm.bnd_p[(item * nthr + (c - 1)) * W + x] = H - ge_p;
                     }
                 }
             }
-            {
-                const int dt = prev_t - prev_p;   // last class: count of (label >= K-1)
-                atomicAdd(&s_thick[nthr], static_cast<unsigned long long>(dt < 0 ? -dt : dt));
+        }
+#pragma unroll
+        for (int j = 0; j < 15; ++j) {
+            if (j < nthr) {
+                unsigned long long a64 = acc_sq[j], b64 = acc_abs[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a64 += __shfl_xor_sync(0xffffffffu, a64, o);
+                    b64 += __shfl_xor_sync(0xffffffffu, b64, o);
+                }
+                if ((tid & 31) == 0) { atomicAdd(&s_sq[j], a64); atomicAdd(&s_abs[j], b64); }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            if (c < K) {
+                unsigned long long a64 = acc_th[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a64 += __shfl_xor_sync(0xffffffffu, a64, o);
+                if ((tid & 31) == 0) atomicAdd(&s_thick[c], a64);
             }
         }
         __syncthreads();
@@ -785,10 +835,7 @@ static int dispatch_np(const LabelPassParams& p, cudaStream_t stream) {
 
 static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
     long long grid = p.n_items < 148 * 8 ? p.n_items : 148 * 8;
-    if (p.K <= 8)
-        label_pass_generic<7><<<static_cast<unsigned>(grid), 256, 0, stream>>>(p);
-    else
-        label_pass_generic<15><<<static_cast<unsigned>(grid), 256, 0, stream>>>(p);
+    label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p);
     return check_launch("label_pass_generic");
 }
 
