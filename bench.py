@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--items M]
 
-A "step" is one pass of the whole suite (fused label pass + contour trace + contour distances)
-over this rank's batch of B-scans, inputs resident in HBM.  One process per GPU (torchrun for N>1),
-B-scans are sharded across ranks with no data-path collective (weak scaling: --items per GPU); a
-single small NCCL all-reduce merges the per-class counts for the dataset-level numbers and is part
-of the timed step.  Rank 0 prints ONE JSON line.
+A "step" is one pass of the whole suite (fused label pass + contour trace + contour distances +
+float64 epilogue) over this rank's batch of B-scans, inputs resident in HBM.  One process per GPU
+(torchrun for N>1), B-scans are sharded across ranks with no data-path collective (weak scaling:
+--items per GPU); a single small NCCL all-reduce merges the per-class counts for the dataset-level
+numbers and is part of the timed step.  Steps are enqueued asynchronously and timed with CUDA events;
+"e2e" is the same suite through suite.evaluate_host on pinned host arrays (H2D inside the timed region,
+metrics read back).  Rank 0 prints ONE JSON line.
 
 --impl reference times the reference's CPU path (the numpy oracle port of Metrics/*.py, per-class
 per-function Python loops, all host cores) on a bounded sample of the same workload.

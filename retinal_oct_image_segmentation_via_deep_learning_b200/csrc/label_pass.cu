@@ -8,24 +8,26 @@
 // plus the build-defined boundary positions b_k(x) = #{y : L[y][x] < k}  (SURVEY.md 8a-D).
 //
 // FAST KERNEL (W % 16 == 0, W <= 2048, H <= 4096, K <= 8)
-//   * persistent CTAs, one B-scan at a time; a producer warp streams R-row chunks of both maps
-//     into a shared-memory ring with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) signalling
-//     mbarriers; HBM reads are full contiguous rows regardless of how lanes consume them.
-//   * each consumer warp owns a strip of 128 columns for ALL rows of the item: lane = 8 adjacent
-//     columns (one LDS.64 per map), lanes 0-15 take the even row of a row pair, lanes 16-31 the
-//     odd row.  Column state therefore never crosses warps.
-//   * column scan: labels of 4 pixels are packed into a PRMT selector; one PRMT against an 8-entry
-//     byte LUT yields, for 4 pixels at once, the flags [v >= k1] | [v >= k2] << 4 for a PAIR of
-//     thresholds; flags accumulate in nibble counters (flushed every 14 rows into byte counters,
-//     those every 504 rows into uint16 column totals in shared memory).
-//   * confusion matrix: joint code t*8+p per pixel.  A lane whose 8 pixel pairs share one code
-//     (the common case in segmentation maps) adds 8 to its private uint16 histogram column; the
-//     rare mixed lanes are compacted (ballot + popc) into a per-warp queue and drained 32 entries
-//     at a time, one entry per lane, so the scalar path never runs under divergence.
+//   * persistent CTAs, one B-scan at a time, one warp per strip of 128 columns for ALL rows of the
+//     item.  Every warp owns a private shared-memory ring (S stages x 2 maps x R rows x 128 B) that it
+//     fills itself with 2-D TMA tile copies (cp.async.bulk.tensor.2d -> UTMALDG, evict-first) completing
+//     on its own mbarriers: no producer warp, no cross-warp wait inside an item.
+//   * lane = 8 adjacent columns (one LDS.64 per map); lanes 0-15 take the even row of a row pair,
+//     lanes 16-31 the odd row.  Column state therefore never crosses warps.
+//   * column scan: labels of 4 pixels x 2 maps are interleaved into a PRMT selector; one PRMT against
+//     an 8-entry byte LUT (immediate) yields the flags of a PAIR of thresholds; flags accumulate in
+//     nibble counters (IMAD adds on the FMA pipe), flushed every 28 rows into byte counters, those every
+//     504 rows into uint16 column totals in shared memory.
+//   * confusion matrix: joint code t*8+p per pixel.  A lane whose 16 pixel pairs share one code (the
+//     common case in segmentation maps) extends a run counted in a register; runs reach the lane's
+//     private uint16 histogram column when the code changes.  The rare mixed lanes are compacted
+//     (ballot + popc) into a per-warp queue and drained 32 entries at a time, one entry per lane.
+//   * contour seeds: classes are tracked per warp; lanes that meet a new class record its first raster
+//     position with a shared-memory atomicMin.
 //   * per item: column totals -> |thickness diff|, boundary error sums (REDUX warp sums), private
 //     histograms -> K x K counts, one plain store per output element (no global atomics).
 //
-// GENERIC KERNEL: any H, W, K <= 16 (byte loads, shared-memory atomics).  Same outputs.
+// GENERIC KERNEL: any H, W, K <= 16: thread per column, run-length accumulation down the column.
 #include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cstdlib>
