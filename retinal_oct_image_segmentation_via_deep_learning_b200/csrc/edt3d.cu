@@ -36,7 +36,7 @@ struct Edt3Params {
     int D0, D1, D2, cls;
     uint16_t* g;             // [D0][D1][D2]
     uint32_t* h2;            // [D0][D1][D2]
-    uint32_t* hist;          // [nbins]
+    uint32_t* hist;          // [nbins + 1]: bins, then the largest squared distance seen
     uint32_t nbins;
 };
 
@@ -87,6 +87,75 @@ __global__ void __launch_bounds__(128) edt3_pass1_kernel(const Edt3Params prm) {
     }
 }
 
+// The same pass for D2 % 16 == 0 and 16-byte aligned volumes: the five label lines are read 16 voxels at a time
+// (the byte-granular version is bound by the number of load instructions, not by bytes) and g leaves as two
+// 16-byte stores per group; the backward sweep re-reads g group by group.
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, int i) {
+    const uint32_t w = i < 8 ? (i < 4 ? v.x : v.y) : (i < 12 ? v.z : v.w);
+    return (w >> ((i & 3) * 8)) & 0xffu;
+}
+
+__global__ void __launch_bounds__(128) edt3_pass1_vec_kernel(const Edt3Params prm) {
+    const long long lines = static_cast<long long>(prm.D0) * prm.D1;
+    const int D0 = prm.D0, D1 = prm.D1, D2 = prm.D2;
+    const uint32_t cls = static_cast<uint32_t>(prm.cls);
+    const int groups = D2 / 16;
+    for (long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; line < lines;
+         line += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i0 = static_cast<int>(line / D1), i1 = static_cast<int>(line % D1);
+        const long long s0 = static_cast<long long>(D1) * D2;
+        const uint4* c = reinterpret_cast<const uint4*>(prm.src + line * D2);
+        const bool border = i0 == 0 || i0 == D0 - 1 || i1 == 0 || i1 == D1 - 1;
+        const uint4* up = border ? c : reinterpret_cast<const uint4*>(prm.src + line * D2 - s0);
+        const uint4* dn = border ? c : reinterpret_cast<const uint4*>(prm.src + line * D2 + s0);
+        const uint4* lf = border ? c : reinterpret_cast<const uint4*>(prm.src + line * D2 - D2);
+        const uint4* rt = border ? c : reinterpret_cast<const uint4*>(prm.src + line * D2 + D2);
+        uint4* g = reinterpret_cast<uint4*>(prm.g + line * D2);
+        uint32_t dist = kInf16, prev = 0xffffffffu;
+        uint4 cur = __ldg(c);
+        for (int k = 0; k < groups; ++k) {
+            const uint4 nxt = k + 1 < groups ? __ldg(c + k + 1) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            const uint4 u = __ldg(up + k), d = __ldg(dn + k), l = __ldg(lf + k), r = __ldg(rt + k);
+            uint32_t out[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t v = byte_of(cur, i);
+                const uint32_t nx = i < 15 ? byte_of(cur, i + 1) : (nxt.x & 0xffu);
+                bool surf = false;
+                if (v == cls)
+                    surf = border || prev != cls || nx != cls || byte_of(u, i) != cls || byte_of(d, i) != cls ||
+                           byte_of(l, i) != cls || byte_of(r, i) != cls;
+                dist = surf ? 0u : (dist == kInf16 ? kInf16 : min(dist + 1u, 0xfffeu));
+                if (i & 1) out[i >> 1] |= dist << 16;
+                else out[i >> 1] = dist;
+                prev = v;
+            }
+            g[2 * k] = make_uint4(out[0], out[1], out[2], out[3]);
+            g[2 * k + 1] = make_uint4(out[4], out[5], out[6], out[7]);
+            cur = nxt;
+        }
+        dist = kInf16;
+        for (int k = 2 * groups - 1; k >= 0; --k) {           // 8 values per 16-byte group, last to first
+            uint4 w = g[k];
+            uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            bool changed = false;
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                const uint32_t f = (words[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                if (f == 0u) dist = 0u;
+                else if (dist != kInf16) {
+                    dist = min(dist + 1u, 0xfffeu);
+                    if (dist < f) {
+                        words[i >> 1] = (i & 1) ? ((words[i >> 1] & 0x0000ffffu) | (dist << 16)) : ((words[i >> 1] & 0xffff0000u) | dist);
+                        changed = true;
+                    }
+                }
+            }
+            if (changed) g[k] = make_uint4(words[0], words[1], words[2], words[3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ envelope
 // Lower envelope of the parabolas  x -> (x - j)^2 + w(j)  over the finite sites j of one line
 // (Meijster et al.).  s[k] = site of region k, t[k] = first x of region k.  Returns the top index q
@@ -94,31 +163,37 @@ __global__ void __launch_bounds__(128) edt3_pass1_kernel(const Edt3Params prm) {
 template <class W>
 __device__ __forceinline__ int build_envelope(int n, W weight, uint16_t* s, uint16_t* t) {
     int q = -1;
+    long long wtop = 0, itop = 0, ttop = 0;       // weight, site and first x of the top region, kept in registers
     for (int u = 0; u < n; ++u) {
         const long long wu = weight(u);
         if (wu < 0) continue;                                   // infinite site
         while (q >= 0) {
-            const long long x = t[q], i = s[q];
-            const long long fi = (x - i) * (x - i) + weight(static_cast<int>(i));
-            const long long fu = (x - u) * (x - u) + wu;
-            if (fi > fu) --q;
-            else break;
+            const long long fi = (ttop - itop) * (ttop - itop) + wtop;
+            const long long fu = (ttop - u) * (ttop - u) + wu;
+            if (fi <= fu) break;
+            --q;                                                // u is lower over the whole top region: pop it
+            if (q >= 0) {
+                itop = s[q];
+                ttop = t[q];
+                wtop = weight(static_cast<int>(itop));
+            }
         }
         if (q < 0) {
             q = 0;
             s[0] = static_cast<uint16_t>(u);
             t[0] = 0;
+            itop = u; ttop = 0; wtop = wu;
         } else {
-            const long long i = s[q];
-            // first x at which u's parabola is strictly... Meijster: Sep(i, u) = (u^2 - i^2 + w(u) - w(i)) div (2 (u - i))
-            const long long num = static_cast<long long>(u) * u - i * i + wu - weight(static_cast<int>(i));
-            const long long den = 2 * (u - i);
-            long long sep = num >= 0 ? num / den : -((-num + den - 1) / den);       // floor division
+            // Meijster: Sep(i, u) = (u^2 - i^2 + w(u) - w(i)) div (2 (u - i)); u takes over from x = Sep + 1
+            const long long num = static_cast<long long>(u) * u - itop * itop + wu - wtop;
+            const long long den = 2 * (u - itop);
+            const long long sep = num >= 0 ? num / den : -((-num + den - 1) / den);       // floor division
             const long long w = sep + 1;
             if (w < n) {
                 ++q;
                 s[q] = static_cast<uint16_t>(u);
                 t[q] = static_cast<uint16_t>(w < 0 ? 0 : w);
+                itop = u; ttop = w < 0 ? 0 : w; wtop = wu;
             }
         }
     }
@@ -144,10 +219,16 @@ __global__ void __launch_bounds__(128) edt3_pass2_kernel(const Edt3Params prm) {
             for (int x = 0; x < D1; ++x) h[static_cast<long long>(x) * D2] = kInf32;
             continue;
         }
+        long long i = s[q], wi = weight(static_cast<int>(i));
+        int tq = t[q];
         for (int x = D1 - 1; x >= 0; --x) {
-            const long long i = s[q];
-            h[static_cast<long long>(x) * D2] = static_cast<uint32_t>((x - i) * (x - i) + weight(static_cast<int>(i)));
-            if (x == t[q]) --q;
+            h[static_cast<long long>(x) * D2] = static_cast<uint32_t>((x - i) * (x - i) + wi);
+            if (x == tq && q > 0) {
+                --q;
+                i = s[q];
+                tq = t[q];
+                wi = weight(static_cast<int>(i));
+            }
         }
     }
 }
@@ -160,6 +241,7 @@ __global__ void __launch_bounds__(128) edt3_pass3_kernel(const Edt3Params prm) {
     for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     uint16_t s[kMaxLine], t[kMaxLine];
+    uint32_t big = 0;                                   // largest squared distance this thread sent to the global bins
     for (long long line = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; line < plane;
          line += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int i1 = static_cast<int>(line / D2), i2 = static_cast<int>(line % D2);
@@ -170,21 +252,37 @@ __global__ void __launch_bounds__(128) edt3_pass3_kernel(const Edt3Params prm) {
         };
         int q = build_envelope(D0, weight, s, t);
         if (q < 0) continue;                                                        // no source surface at all
+        long long i = s[q], wi = weight(static_cast<int>(i));
+        int tq = t[q];
         for (int x = D0 - 1; x >= 0; --x) {
             if (surface_at(prm.qry, D0, D1, D2, x, i1, i2, cls)) {
-                const long long i = s[q];
-                const uint32_t d2 = static_cast<uint32_t>((x - i) * (x - i) + weight(static_cast<int>(i)));
+                const uint32_t d2 = static_cast<uint32_t>((x - i) * (x - i) + wi);
                 if (d2 < static_cast<uint32_t>(kSmemBins)) atomicAdd(&s_hist[d2], 1u);
-                else atomicAdd(&prm.hist[min(d2, prm.nbins - 1)], 1u);
+                else {
+                    atomicAdd(&prm.hist[min(d2, prm.nbins - 1)], 1u);
+                    big = max(big, min(d2, prm.nbins - 1));
+                }
             }
-            if (x == t[q]) --q;
+            if (x == tq && q > 0) {
+                --q;
+                i = s[q];
+                tq = t[q];
+                wi = weight(static_cast<int>(i));
+            }
         }
     }
     __syncthreads();
+    uint32_t top = 0;                                   // largest non-empty shared bin of this CTA
     for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) {
         const uint32_t c = s_hist[i];
-        if (c && static_cast<uint32_t>(i) < prm.nbins) atomicAdd(&prm.hist[i], c);
+        if (c && static_cast<uint32_t>(i) < prm.nbins) {
+            atomicAdd(&prm.hist[i], c);
+            top = i;
+        }
     }
+    top = max(top, big);
+    top = __reduce_max_sync(0xffffffffu, top);
+    if ((threadIdx.x & 31) == 0 && top) atomicMax(&prm.hist[prm.nbins], top);      // slot [nbins]: upper bound of the scan
 }
 
 // query-surface count when the source surface is empty is not needed: the metrics are undefined then.
@@ -204,7 +302,7 @@ __global__ void __launch_bounds__(1024) edt3_select_kernel(const Sel3Params prm)
     __shared__ uint32_t s_max[32];
     __shared__ uint32_t s_sel[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n = prm.nbins;
+    const uint32_t n = min(prm.nbins, prm.hist[prm.nbins] + 1u);      // bins above the largest distance seen are empty
     const uint32_t chunk = (n + 1023u) / 1024u;
     const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
     unsigned long long cnt = 0;
@@ -266,7 +364,7 @@ extern "C" size_t octm_surface3d_workspace_bytes(int D0, int D1, int D2) {
     if (D0 < 1 || D1 < 1 || D2 < 1) return 0;
     const size_t vox = static_cast<size_t>(D0) * D1 * D2;
     auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
-    return up(vox * 2) + up(vox * 4) + up(static_cast<size_t>(edt3_nbins(D0, D1, D2)) * 4);
+    return up(vox * 2) + up(vox * 4) + up((static_cast<size_t>(edt3_nbins(D0, D1, D2)) + 1) * 4);
 }
 
 extern "C" int octm_surface3d_u8(const uint8_t* y_true, const uint8_t* y_pred, int D0, int D1, int D2, int num_classes,
@@ -296,14 +394,17 @@ extern "C" int octm_surface3d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
         const int cls = unit >> 1, dir = unit & 1;
         // direction 0: queries = y_pred surface, sources = y_true surface (d1 of the reference); 1 swapped
         octm::Edt3Params p{dir == 0 ? y_true : y_pred, dir == 0 ? y_pred : y_true, D0, D1, D2, cls, g, h2, hist, nbins};
-        if (cudaMemsetAsync(hist, 0, static_cast<size_t>(nbins) * 4, st) != cudaSuccess)
+        if (cudaMemsetAsync(hist, 0, (static_cast<size_t>(nbins) + 1) * 4, st) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "memset(hist) failed");
         auto blocks = [&](long long threads) {
             long long b = (threads + 127) / 128;
             const long long cap = static_cast<long long>(sms) * 16;
             return static_cast<unsigned>(b < cap ? b : cap);
         };
-        octm::edt3_pass1_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
+        if (D2 % 16 == 0 && reinterpret_cast<uintptr_t>(p.src) % 16 == 0)
+            octm::edt3_pass1_vec_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
+        else
+            octm::edt3_pass1_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
         if (int e = octm::check_launch("edt3_pass1_kernel")) return e;
         octm::edt3_pass2_kernel<<<blocks(1ll * D0 * D2), 128, 0, st>>>(p);
         if (int e = octm::check_launch("edt3_pass2_kernel")) return e;

@@ -45,6 +45,18 @@ def test_random_blobs_and_missing_class(cuda):
     _check(vt, vp, 4, cuda)                            # class 3 absent from both
 
 
+def test_vectorised_first_pass_shapes(cuda):
+    """D2 a multiple of 16: the 16-voxel first pass (borders, thin sheets, runs crossing group boundaries)"""
+    rng = np.random.default_rng(54)
+    for shape in ((12, 9, 32), (7, 11, 48), (5, 6, 16)):
+        vt = (rng.random(shape) < 0.5).astype(np.uint8)
+        vp = (rng.random(shape) < 0.5).astype(np.uint8)
+        vt[:, :, 10:20] = 1                                # long run along the contiguous axis
+        _check(vt, vp, 2, cuda)
+    vt, vp = synth.layered_volume_pair(40, 24, 32, 4, seed=55)
+    _check(vt, vp, 4, cuda)
+
+
 def test_far_apart_and_border_touching(cuda):
     vt = np.zeros((40, 30, 12), np.uint8)
     vp = np.zeros((40, 30, 12), np.uint8)
