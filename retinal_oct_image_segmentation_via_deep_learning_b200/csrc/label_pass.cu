@@ -24,8 +24,9 @@
 //     (ballot + popc) into a per-warp queue and drained 32 entries at a time, one entry per lane.
 //   * contour seeds: classes are tracked per warp; lanes that meet a new class record its first raster
 //     position with a shared-memory atomicMin.
-//   * per item: column totals -> |thickness diff|, boundary error sums (REDUX warp sums), private
-//     histograms -> K x K counts, one plain store per output element (no global atomics).
+//   * per item and warp: column totals -> |thickness diff|, boundary error sums (REDUX warp sums), private
+//     histograms -> K x K counts; the strips of an item meet in the zero-initialised outputs through
+//     global reductions (a few dozen RED per warp and item), never at a CTA barrier.
 //
 // GENERIC KERNEL: any H, W, K <= 16: thread per column, run-length accumulation down the column.
 #include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -62,16 +63,11 @@ struct LabelPassParams {
 
 // shared-memory carve-up of the fast kernel
 
-constexpr int kOffCounts = 128;                // u32[256]
-constexpr int kOffSq = kOffCounts + 1024;      // u64[16]
-constexpr int kOffAbs = kOffSq + 128;          // u64[16]
-constexpr int kOffThick = kOffAbs + 128;       // u64[16]
-constexpr int kOffFirst = kOffThick + 128;     // u32[2][16]
-constexpr int kOffWarp = 2048;
+constexpr int kOffWarp = 0;          // no CTA-wide block any more: warps are autonomous
 constexpr int kWarpTotals = 2 * 8 * kStrip * 2;    // u16 [map][thr][128]
 constexpr int kWarpHist = 64 * 32 * 2;             // u16 [code][lane]
 constexpr int kWarpQueue = kQueueCap * 16;         // uint4 entries
-constexpr int kWarpBars = 128;                     // the warp's S "stage full" mbarriers
+constexpr int kWarpBars = 256;                     // the warp's S "stage full" mbarriers (64 B) + first-position table (128 B at +128)
 constexpr int kWarpBytesShort = kWarpHist + kWarpQueue;              // H <= 504: totals alias the histogram block
 constexpr int kWarpBytesTall = kWarpHist + kWarpQueue + kWarpTotals;
 constexpr int kShortRows = 504;   // 18 byte flushes x 7 nibble flushes x 4 rows
@@ -204,7 +200,7 @@ __device__ __forceinline__ uint32_t first_match8(uint2 w, uint32_t cc) {
 // a lane met classes `fresh` (bits as presence_bits) for the first time in this item: fold the raster
 // position of their first pixel among its rows A (at posA) and B (at posB) into the CTA's table
 __device__ __forceinline__ void record_first(uint32_t fresh, uint2 tA, uint2 pA, uint2 tB, uint2 pB, uint32_t posA,
-                                             uint32_t posB, uint32_t* cta_first) {
+                                             uint32_t posB, uint32_t* first_tab) {
     while (fresh) {
         const int bit = __ffs(fresh) - 1;
         fresh &= fresh - 1;
@@ -215,7 +211,7 @@ __device__ __forceinline__ void record_first(uint32_t fresh, uint2 tA, uint2 pA,
             i = first_match8(m ? pB : tB, cc);
             pos = posB + i;
         }
-        if (i < 8 && pos < cta_first[m * 16 + c]) atomicMin(&cta_first[m * 16 + c], pos);
+        if (i < 8 && pos < first_tab[m * 16 + c]) atomicMin(&first_tab[m * 16 + c], pos);
     }
 }
 
@@ -280,7 +276,7 @@ struct StageConsts {
     unsigned short* hist_lane;
     uint4* queue;
     unsigned short* totals;
-    uint32_t* cta_first;
+    uint32_t* first_tab;
 };
 
 // One ring stage (rows x strip) of one consumer warp.  Each pass of the loop takes 4 rows: lanes 0-15 rows
@@ -338,7 +334,7 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
                     const uint32_t any_fresh = __reduce_or_sync(0xffffffffu, fresh);
                     if (any_fresh) {
                         ls.warp_seen |= any_fresh;
-                        if (fresh) record_first(fresh, tA, pA, tB, pB, pos, pos + sc.W2, sc.cta_first);
+                        if (fresh) record_first(fresh, tA, pA, tB, pB, pos, pos + sc.W2, sc.first_tab);
                     }
                 }
                 __syncwarp();
@@ -366,7 +362,8 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
 //   [ S full-barriers, padded to 128 B | histogram 4 KB | queue 1 KB | (H > 504: column totals 4 KB) | ring ]
 // The ring is PRIVATE to the warp: S stages x 2 maps x R rows x strip bytes, filled by 2-D TMA tile copies
 // (one box of R rows x 128 columns per map) that the warp issues for itself.  Warps of a CTA therefore
-// never wait for each other inside an item; they meet only in the item epilogue.
+// never wait for each other: each folds its strip's results into the zero-initialised outputs with global
+// reductions (RED.ADD / RED.MIN), so a CTA has no barrier after its start-up.
 template <int NP, bool CONF, bool COLS, bool SEEDS, bool WIDE>
 __global__ void __launch_bounds__(WIDE ? 16 * 32 : 8 * 32, WIDE ? 1 : OCTM_LP_MINB)
 label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap tm_true, const __grid_constant__ CUtensorMap tm_pred) {
@@ -375,11 +372,6 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     const int NW = blockDim.x >> 5;
     const int H = prm.H, W = prm.W, K = prm.K, R = prm.R, S = prm.S;
 
-    uint32_t* cta_counts = reinterpret_cast<uint32_t*>(smem + kOffCounts);
-    unsigned long long* cta_sq = reinterpret_cast<unsigned long long*>(smem + kOffSq);
-    unsigned long long* cta_abs = reinterpret_cast<unsigned long long*>(smem + kOffAbs);
-    unsigned long long* cta_thick = reinterpret_cast<unsigned long long*>(smem + kOffThick);
-    uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + kOffFirst);
     const bool tall = H > kShortRows;
     const uint32_t srow = static_cast<uint32_t>(min(W, kStrip));          // bytes per staged strip row
     const uint32_t map_bytes = static_cast<uint32_t>(R) * srow;
@@ -387,13 +379,11 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     const int state_bytes = kWarpBars + (tall ? kWarpBytesTall : kWarpBytesShort);
     const int warp_bytes = state_bytes + S * static_cast<int>(stage_bytes);   // multiple of 128
 
-    for (int i = tid; i < 256; i += blockDim.x) cta_counts[i] = 0;
-    if (tid < 16) cta_sq[tid] = cta_abs[tid] = cta_thick[tid] = 0;
-    if (tid < 32) cta_first[tid] = OCTM_NO_SEED;
     uint8_t* wbase = smem + kOffWarp + warp * warp_bytes;
     for (int i = lane; i < state_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(wbase)[i] = 0;
     const uint32_t bars = smem_u32(wbase);                                  // full[s] at bars + 8 s
     const uint32_t ring_addr = bars + state_bytes;
+    uint32_t* warp_first = reinterpret_cast<uint32_t*>(wbase + 128);        // [2][16] first raster position per class
     if (lane == 0) {
         for (int s = 0; s < S; ++s) mbar_init_a(bars + 8 * s, 1);
         mbar_fence_init();
@@ -431,7 +421,6 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     const bool colv = col < W;
     const bool strip_full = (warp + 1) * kStrip <= W;      // warp-uniform
     const int nthr = K - 1;
-    const int consumers = NW * 32;
     const uint32_t lane_smem = static_cast<uint32_t>(phase) * srow + (lane & 15) * 8;     // inside a staged strip
     const uint32_t lane_pos = static_cast<uint32_t>(phase) * W + col;                       // inside the image
 
@@ -439,11 +428,15 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     sc.srow2 = 2u * srow; sc.srow4 = 4u * srow; sc.W2 = 2u * W; sc.W4 = 4u * W;
     sc.map_bytes = map_bytes; sc.one = prm.one; sc.all_classes = ((1u << K) - 1u) * 0x101u;
     sc.phase = phase; sc.lane = lane; sc.colv = colv;
-    sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.cta_first = cta_first;
+    sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.first_tab = warp_first;
     LaneState<NP> ls;
     uint32_t s = 0, ph = 0;
     for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
         ls.reset(COLS);
+        if (SEEDS) {
+            warp_first[lane] = OCTM_NO_SEED;
+            __syncwarp();
+        }
 
         for (int r0 = 0; r0 < H; r0 += R) {
             const int rows = min(R, H - r0);
@@ -487,7 +480,10 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
                     lo += w & 0xffffu;
                     hi += w >> 16;
                 }
-                if (lo + hi) atomicAdd(&cta_counts[code], lo + hi);
+                // this warp's share of cm[t][p] joins the other strips' in the (zero-initialised) output
+                const int t = code >> 3, pp = code & 7;
+                if ((lo + hi) && t < K && pp < K)
+                    atomicAdd(prm.counts + (item * K + t) * K + pp, static_cast<unsigned long long>(lo + hi));
             }
         }
 
@@ -545,8 +541,8 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
                     const uint32_t s1 = __reduce_add_sync(0xffffffffu, sq[j]);
                     const uint32_t s2 = __reduce_add_sync(0xffffffffu, ab[j]);
                     if (lane == 0) {
-                        atomicAdd(&cta_sq[j], static_cast<unsigned long long>(s1));
-                        atomicAdd(&cta_abs[j], static_cast<unsigned long long>(s2));
+                        if (prm.bsq != nullptr && s1) atomicAdd(reinterpret_cast<unsigned long long*>(prm.bsq) + item * nthr + j, static_cast<unsigned long long>(s1));
+                        if (prm.babs != nullptr && s2) atomicAdd(reinterpret_cast<unsigned long long*>(prm.babs) + item * nthr + j, static_cast<unsigned long long>(s2));
                     }
                 }
             }
@@ -554,36 +550,17 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
             for (int c = 0; c < 2 * NP + 1; ++c) {
                 if (c < K) {
                     const uint32_t s3 = __reduce_add_sync(0xffffffffu, th[c]);
-                    if (lane == 0) atomicAdd(&cta_thick[c], static_cast<unsigned long long>(s3));
+                    if (lane == 0 && prm.thick != nullptr && s3)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(prm.thick) + item * K + c, static_cast<unsigned long long>(s3));
                 }
             }
         }
-        named_bar_sync(1, consumers);
-        {
-            const int ct_id = warp * 32 + lane;
-            if (prm.counts != nullptr) {
-                for (int i = ct_id; i < K * K; i += consumers) {
-                    const int code = (i / K) * 8 + (i % K);
-                    prm.counts[item * K * K + i] = cta_counts[code];
-                }
-            }
-            if (CONF)
-                for (int i = ct_id; i < 64; i += consumers) cta_counts[i] = 0;
-            if (ct_id < 16) {
-                if (COLS) {
-                    if (ct_id < K && prm.thick != nullptr) prm.thick[item * K + ct_id] = static_cast<long long>(cta_thick[ct_id]);
-                    if (ct_id < nthr && prm.bsq != nullptr) prm.bsq[item * nthr + ct_id] = static_cast<long long>(cta_sq[ct_id]);
-                    if (ct_id < nthr && prm.babs != nullptr) prm.babs[item * nthr + ct_id] = static_cast<long long>(cta_abs[ct_id]);
-                    cta_thick[ct_id] = cta_sq[ct_id] = cta_abs[ct_id] = 0;
-                }
-            }
-            if (SEEDS && ct_id < 32) {
-                const int m = ct_id >> 4, c = ct_id & 15;
-                if (c < K && prm.first_pos != nullptr) prm.first_pos[(item * 2 + m) * K + c] = cta_first[ct_id];
-                cta_first[ct_id] = OCTM_NO_SEED;
-            }
+        if (SEEDS && prm.first_pos != nullptr) {
+            __syncwarp();
+            const int m = lane >> 4, c = lane & 15;
+            const uint32_t v = warp_first[lane];
+            if (c < K && v != OCTM_NO_SEED) atomicMin(prm.first_pos + (item * 2 + m) * K + c, v);
         }
-        named_bar_sync(1, consumers);
     }
 }
 
@@ -805,6 +782,17 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     p.S = S;
     const int smem = kOffWarp + NW * (state + S * stage);
     if (smem > budget) return fail(OCTM_ERR_UNSUPPORTED, "label pass: %d B of shared memory needed", smem);
+    // the warps of a CTA merge their strips in the outputs by global reductions: start from zero / "no seed"
+    {
+        const size_t n = static_cast<size_t>(p.n_items), k = static_cast<size_t>(p.K);
+        bool ok = true;
+        if (p.counts) ok = ok && cudaMemsetAsync(p.counts, 0, n * k * k * 8, stream) == cudaSuccess;
+        if (p.thick) ok = ok && cudaMemsetAsync(p.thick, 0, n * k * 8, stream) == cudaSuccess;
+        if (p.bsq) ok = ok && cudaMemsetAsync(p.bsq, 0, n * (k - 1) * 8, stream) == cudaSuccess;
+        if (p.babs) ok = ok && cudaMemsetAsync(p.babs, 0, n * (k - 1) * 8, stream) == cudaSuccess;
+        if (p.first_pos) ok = ok && cudaMemsetAsync(p.first_pos, 0xff, n * 2 * k * 4, stream) == cudaSuccess;
+        if (!ok) return fail(OCTM_ERR_LAUNCH, "label pass: clearing the outputs failed");
+    }
     CUtensorMap tm_true, tm_pred;
     const long long rows = p.n_items * p.H;
     if (int e = make_label_map(&tm_true, p.yt, rows, p.W, R)) return e;
