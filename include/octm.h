@@ -157,8 +157,10 @@ OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int
  *   verts   uint32 [n][K][2][max_pts]  packed (y2 << 16 | x2) doubled-lattice vertices in trace
  *                                      order (the closing repeat, if any, is the last entry)
  *   d2      uint32 [n][K][2][max_pts]  per-query-vertex D2: [i][c][d][j] = squared distance from vertex j
- *                                      of map 1-d to the nearest vertex of map d.  Required: it is also
- *                                      the scratch between the search and the select kernel. */
+ *                                      of map 1-d to the nearest vertex of map d.  Required.  With
+ *                                      keep_d2 == 0 it is scratch and its contents are unspecified on
+ *                                      return (the search kernel counts most units' distances in
+ *                                      shared memory instead of storing them); keep_d2 != 0 stores all. */
 OCTM_API int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t item_elems, int num_classes,
                       uint32_t* first_pos /* [n][K] */, void* stream);
 OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H,
@@ -166,7 +168,7 @@ OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pre
                             uint32_t* verts, uint32_t* n_pts, uint32_t* flags, void* stream);
 OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items,
                             int num_classes, int max_pts, uint32_t* max_sq, uint32_t* p95_sq,
-                            double* sum_dist, uint32_t* d2, void* stream);
+                            double* sum_dist, uint32_t* d2, int keep_d2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 3-D surface-distance metrics (BASELINE config 5; the reference's contour metrics are 2-D only, this is

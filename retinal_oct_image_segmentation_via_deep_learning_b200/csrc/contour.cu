@@ -522,7 +522,14 @@ struct SearchParams {
     int max_pts;
     int tile;                // source vertices staged per pass, multiple of kBox
     uint32_t* d2;            // [n][K][2][max_pts]
+    uint32_t* max_sq;        // [n][K][2]      kNeedsSelect when the unit is left to distance_select_kernel
+    uint32_t* p95_sq;        // [n][K][2][2]
+    double* sum_dist;        // [n][K][2]
+    bool keep_d2;            // store every unit's squared distances as well
 };
+
+constexpr int kCountBins = 1024;                    // squared distances 0, 2, .. 2046 are counted in shared memory
+constexpr uint32_t kNeedsSelect = 0xffffffffu;      // not a squared distance (coordinates are below 2^14)
 
 __device__ __forceinline__ void coop_scan_box(const int4* src4, int bb, int ns, int cy, int cx, int& bm) {
     const int i0 = bb * kBox;
@@ -543,6 +550,10 @@ __device__ __forceinline__ void coop_scan_box(const int4* src4, int bb, int ns, 
 __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_search_kernel(const SearchParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ int s_next;
+    __shared__ uint32_t s_bins[kCountBins / 2];      // two 16-bit counters per word: count of squared distance 2 * h
+    __shared__ uint32_t s_vmax, s_big;
+    for (int i = threadIdx.x; i < kCountBins / 2; i += kSearchThreads) s_bins[i] = 0;
+    if (threadIdx.x == 0) s_vmax = s_big = 0;
     const int cap = prm.max_pts, tile = prm.tile;
     int4* const src4 = reinterpret_cast<int4*>(dsm);                                          // {y, x, y^2+x^2, -}
     int4* const boxes = reinterpret_cast<int4*>(dsm + static_cast<size_t>(tile) * 16);       // {ymin, ymax, xmin, xmax}
@@ -554,7 +565,14 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
         // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
         const int ns_all = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
         const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
-        if (ns_all == 0 || nq == 0) continue;
+        if (ns_all == 0 || nq == 0) {
+            if (threadIdx.x == 0) {
+                prm.max_sq[unit] = 0;
+                prm.p95_sq[unit * 2] = prm.p95_sq[unit * 2 + 1] = 0;
+                prm.sum_dist[unit] = 0.0;
+            }
+            continue;
+        }
         const uint32_t* vs = prm.verts + (pair * 2 + dir) * static_cast<long long>(cap);
         const uint32_t* vq = prm.verts + (pair * 2 + 1 - dir) * static_cast<long long>(cap);
         uint32_t* dq = prm.d2 + unit * static_cast<long long>(cap);
@@ -582,7 +600,7 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
                 src4[i] = make_int4(y, x, y * y + x * x, 0);
             }
             __syncthreads();
-            if (threadIdx.x == 0) s_next = 0;
+            if (threadIdx.x == 0) { s_next = 0; s_vmax = 0; s_big = 0; }
             for (int b = threadIdx.x; b < nb; b += kSearchThreads) {
                 int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
                 const int e = min(ns, (b + 1) * kBox);
@@ -593,6 +611,12 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
                 boxes[b] = make_int4(ymin, ymax, xmin, xmax);
             }
             __syncthreads();
+            // On the last tile the minima are final: they are counted (16-bit counters, one per even value) instead
+            // of stored, and the unit's statistics come from the counters.  A unit with a value the counters cannot
+            // hold repeats the tile's search in store mode and is left to distance_select_kernel.
+            const bool last = t0 + tile >= ns_all;
+            bool count = last && nq <= 0xffff;
+          for (;;) {
             // chunks are handed out dynamically (shared counter): their cost varies with the local geometry
             for (;;) {
                 int c = 0;
@@ -640,7 +664,68 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
                     }
                     bmax = __reduce_max_sync(0xffffffffu, bestd);
                 }
-                if (j < nq) dq[j] = static_cast<uint32_t>(bestd);
+                if ((!count || prm.keep_d2) && j < nq) dq[j] = static_cast<uint32_t>(bestd);
+                if (!count) continue;
+                const uint32_t dv = static_cast<uint32_t>(bestd), h = dv >> 1;
+                const bool ok = j < nq && (dv & 1u) == 0 && h < static_cast<uint32_t>(kCountBins);
+                const uint32_t peers = __match_any_sync(0xffffffffu, ok ? h : static_cast<uint32_t>(kCountBins) + lane);
+                if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_bins[h >> 1], static_cast<uint32_t>(__popc(peers)) << ((h & 1u) * 16));
+                const uint32_t wmax = __reduce_max_sync(0xffffffffu, j < nq ? dv : 0u);
+                const bool bad = __any_sync(0xffffffffu, j < nq && !ok);
+                if (lane == 0) {
+                    atomicMax(&s_vmax, wmax);
+                    if (bad) s_big = 1;
+                }
+            }
+            if (!count) break;
+            __syncthreads();                       // counters, s_vmax, s_big complete
+            if (s_big == 0) break;
+            count = false;                         // CTA-uniform: search the tile again, storing
+            if (threadIdx.x == 0) s_next = 0;
+            __syncthreads();
+          }
+            if (!last) continue;
+            if (warp != 0) continue;
+            if (!count) {                          // stored: hand the unit to the select kernel
+                if (lane == 0) prm.max_sq[unit] = kNeedsSelect;
+                if (nq <= 0xffff)
+                    for (int i = lane; i < kCountBins / 2; i += 32) s_bins[i] = 0;
+                continue;
+            }
+            // warp 0: order statistics, maximum and sum of distances from the counters (cleared on the way);
+            // the next unit's first counter update is two CTA barriers away
+            const uint32_t vmax = s_vmax;
+            const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);     // numpy linear percentile
+            const uint32_t lo = static_cast<uint32_t>(floor(pos));
+            const uint32_t hi = lo + 1 < static_cast<uint32_t>(nq) ? lo + 1 : lo;
+            uint32_t v_lo = 0, v_hi = 0, base = 0;
+            double dsum = 0.0;
+            for (uint32_t h0 = 0; h0 <= (vmax >> 1); h0 += 32) {
+                const uint32_t h = h0 + lane;
+                const uint32_t cnt = (s_bins[h >> 1] >> ((h & 1u) * 16)) & 0xffffu;
+                __syncwarp();
+                if ((lane & 1) == 0) s_bins[h >> 1] = 0;
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const uint32_t first = base + incl - cnt;                    // ranks [first, first + cnt) hold value 2 h
+                const uint32_t m_lo = __ballot_sync(0xffffffffu, cnt != 0 && first <= lo && lo < first + cnt);
+                const uint32_t m_hi = __ballot_sync(0xffffffffu, cnt != 0 && first <= hi && hi < first + cnt);
+                if (m_lo) v_lo = 2 * (h0 + __ffs(m_lo) - 1);
+                if (m_hi) v_hi = 2 * (h0 + __ffs(m_hi) - 1);
+                if (cnt) dsum = __dadd_rn(dsum, __dmul_rn(static_cast<double>(cnt), sqrt(static_cast<double>(2 * h) / 4.0)));
+                base += __shfl_sync(0xffffffffu, incl, 31);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dsum = __dadd_rn(dsum, __shfl_xor_sync(0xffffffffu, dsum, o));
+            if (lane == 0) {
+                prm.max_sq[unit] = vmax;
+                prm.p95_sq[unit * 2 + 0] = v_lo;
+                prm.p95_sq[unit * 2 + 1] = v_hi;
+                prm.sum_dist[unit] = dsum;
             }
         }
     }
@@ -716,16 +801,8 @@ __global__ void __launch_bounds__(128) distance_select_kernel(const SelectParams
          unit += static_cast<long long>(gridDim.x) * 4) {
         const long long pair = unit >> 1;
         const int dir = static_cast<int>(unit & 1);
-        const int ns = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
+        if (prm.max_sq[unit] != kNeedsSelect) continue;         // finished by the search kernel (the usual case)
         const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
-        if (ns == 0 || nq == 0) {
-            if (lane == 0) {
-                prm.max_sq[unit] = 0;
-                prm.p95_sq[unit * 2] = prm.p95_sq[unit * 2 + 1] = 0;
-                prm.sum_dist[unit] = 0.0;
-            }
-            continue;
-        }
         const uint32_t* dq = prm.d2 + unit * static_cast<long long>(cap);
         uint32_t vmax = 0;
         double dsum = 0.0;
@@ -839,7 +916,7 @@ static size_t dist_smem(int max_pts) {
 
 extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
                                        int max_pts, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
-                                       uint32_t* d2, void* stream) {
+                                       uint32_t* d2, int keep_d2, void* stream) {
     if (n_items < 0 || num_classes < 1 || max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "bad shape");
     if (n_items == 0) return OCTM_OK;
     if (!verts || !n_pts || !max_sq || !p95_sq || !sum_dist) return octm::fail(OCTM_ERR_INVALID, "null pointer");
@@ -864,7 +941,7 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
         if (cudaFuncSetAttribute(octm::distance_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_search_kernel) failed");
-        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2};
+        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0};
         long long grid = n_pairs * 2;
         const long long cap = static_cast<long long>(octm::sm_count()) * 32;
         if (grid > cap) grid = cap;
@@ -928,5 +1005,5 @@ extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
     if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, max_pts, verts, n_pts,
                                         flags, stream))
         return e;
-    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, max_sq, p95_sq, sum_dist, d2_ws, stream);
+    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, max_sq, p95_sq, sum_dist, d2_ws, 0, stream);
 }

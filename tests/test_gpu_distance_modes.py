@@ -26,6 +26,11 @@ for name, (yt, yp), k in [("layered", synth.layered_pair(3, 200, 256, 6, seed=71
     for i in range(sq.shape[0]):
         for c in range(k):
             tot += int(sq[i, c, 0, :n[i, c, 1]].astype(np.int64).sum()) * 7 + int(sq[i, c, 1, :n[i, c, 0]].astype(np.int64).sum())
+    # without return_sq the search kernel counts the distances instead of storing them: same integers, sums
+    # equal up to the order of the float64 additions
+    ct2 = suite.contour_pass(torch.from_numpy(yt).to(dev), torch.from_numpy(yp).to(dev), k)
+    assert torch.equal(ct2.max_sq, ct.max_sq) and torch.equal(ct2.p95_sq, ct.p95_sq), name
+    np.testing.assert_allclose(ct2.sum_dist.cpu().numpy(), ct.sum_dist.cpu().numpy(), rtol=1e-12)
     out[name] = [tot, ct.max_sq.cpu().numpy().view(np.uint32).tolist(), ct.p95_sq.cpu().numpy().view(np.uint32).tolist()]
 print(json.dumps(out))
 """ % ROOT
