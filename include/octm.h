@@ -167,8 +167,9 @@ OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pre
                             int W, int num_classes, const uint32_t* first_pos, int max_pts,
                             uint32_t* verts, uint32_t* n_pts, uint32_t* flags, void* stream);
 OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items,
-                            int num_classes, int max_pts, uint32_t* max_sq, uint32_t* p95_sq,
-                            double* sum_dist, uint32_t* d2, int keep_d2, void* stream);
+                            int num_classes, int max_pts, int H, int W /* shape the vertices were traced on */,
+                            uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, uint32_t* d2, int keep_d2,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 3-D surface-distance metrics (BASELINE config 5; the reference's contour metrics are 2-D only, this is

@@ -531,6 +531,62 @@ struct SearchParams {
 constexpr int kCountBins = 1024;                    // squared distances 0, 2, .. 2046 are counted in shared memory
 constexpr uint32_t kNeedsSelect = 0xffffffffu;      // not a squared distance (coordinates are below 2^14)
 
+// Counting form of the per-unit statistics (shared by both search kernels).  Squared distances between contour
+// vertices are even (a vertex has exactly one odd doubled-lattice coordinate), so value 2 h is counted in 16-bit
+// counter h, two counters per word.  Equal values of a warp are merged with MATCH.ANY: one shared-memory atomic
+// per distinct value.  A value the counters cannot hold raises *s_big.
+__device__ __forceinline__ void count_minima(int bestd, bool valid, int lane, uint32_t* s_bins, uint32_t* s_vmax,
+                                             uint32_t* s_big) {
+    const uint32_t dv = static_cast<uint32_t>(bestd), h = dv >> 1;
+    const bool ok = valid && (dv & 1u) == 0 && h < static_cast<uint32_t>(kCountBins);
+    const uint32_t peers = __match_any_sync(0xffffffffu, ok ? h : static_cast<uint32_t>(kCountBins) + lane);
+    if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_bins[h >> 1], static_cast<uint32_t>(__popc(peers)) << ((h & 1u) * 16));
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, valid ? dv : 0u);
+    const bool bad = __any_sync(0xffffffffu, valid && !ok);
+    if (lane == 0) {
+        atomicMax(s_vmax, wmax);
+        if (bad) *s_big = 1;
+    }
+}
+
+// One warp: maximum, the two neighbours of numpy's linear 95th percentile and sum of sqrt(D2 / 4) (float64, one
+// square root per distinct value, fixed order) of the nq counted values; the counters are left cleared.
+__device__ __forceinline__ void stats_from_counters(uint32_t* s_bins, uint32_t vmax, int nq, int lane, uint32_t* max_sq,
+                                                    uint32_t* p95_sq, double* sum_dist) {
+    const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);     // virtual index (m - 1) * 0.95
+    const uint32_t lo = static_cast<uint32_t>(floor(pos));
+    const uint32_t hi = lo + 1 < static_cast<uint32_t>(nq) ? lo + 1 : lo;
+    uint32_t v_lo = 0, v_hi = 0, base = 0;
+    double dsum = 0.0;
+    for (uint32_t h0 = 0; h0 <= (vmax >> 1); h0 += 32) {
+        const uint32_t h = h0 + lane;
+        const uint32_t cnt = (s_bins[h >> 1] >> ((h & 1u) * 16)) & 0xffffu;
+        __syncwarp();
+        if ((lane & 1) == 0) s_bins[h >> 1] = 0;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const uint32_t first = base + incl - cnt;                    // ranks [first, first + cnt) hold value 2 h
+        const uint32_t m_lo = __ballot_sync(0xffffffffu, cnt != 0 && first <= lo && lo < first + cnt);
+        const uint32_t m_hi = __ballot_sync(0xffffffffu, cnt != 0 && first <= hi && hi < first + cnt);
+        if (m_lo) v_lo = 2 * (h0 + __ffs(m_lo) - 1);
+        if (m_hi) v_hi = 2 * (h0 + __ffs(m_hi) - 1);
+        if (cnt) dsum = __dadd_rn(dsum, __dmul_rn(static_cast<double>(cnt), sqrt(static_cast<double>(2 * h) / 4.0)));
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum = __dadd_rn(dsum, __shfl_xor_sync(0xffffffffu, dsum, o));
+    if (lane == 0) {
+        *max_sq = vmax;
+        p95_sq[0] = v_lo;
+        p95_sq[1] = v_hi;
+        *sum_dist = dsum;
+    }
+}
+
 __device__ __forceinline__ void coop_scan_box(const int4* src4, int bb, int ns, int cy, int cx, int& bm) {
     const int i0 = bb * kBox;
     if (i0 + kBox <= ns) {
@@ -666,16 +722,7 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
                 }
                 if ((!count || prm.keep_d2) && j < nq) dq[j] = static_cast<uint32_t>(bestd);
                 if (!count) continue;
-                const uint32_t dv = static_cast<uint32_t>(bestd), h = dv >> 1;
-                const bool ok = j < nq && (dv & 1u) == 0 && h < static_cast<uint32_t>(kCountBins);
-                const uint32_t peers = __match_any_sync(0xffffffffu, ok ? h : static_cast<uint32_t>(kCountBins) + lane);
-                if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_bins[h >> 1], static_cast<uint32_t>(__popc(peers)) << ((h & 1u) * 16));
-                const uint32_t wmax = __reduce_max_sync(0xffffffffu, j < nq ? dv : 0u);
-                const bool bad = __any_sync(0xffffffffu, j < nq && !ok);
-                if (lane == 0) {
-                    atomicMax(&s_vmax, wmax);
-                    if (bad) s_big = 1;
-                }
+                count_minima(bestd, j < nq, lane, s_bins, &s_vmax, &s_big);
             }
             if (!count) break;
             __syncthreads();                       // counters, s_vmax, s_big complete
@@ -692,42 +739,193 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
                     for (int i = lane; i < kCountBins / 2; i += 32) s_bins[i] = 0;
                 continue;
             }
-            // warp 0: order statistics, maximum and sum of distances from the counters (cleared on the way);
-            // the next unit's first counter update is two CTA barriers away
-            const uint32_t vmax = s_vmax;
-            const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);     // numpy linear percentile
-            const uint32_t lo = static_cast<uint32_t>(floor(pos));
-            const uint32_t hi = lo + 1 < static_cast<uint32_t>(nq) ? lo + 1 : lo;
-            uint32_t v_lo = 0, v_hi = 0, base = 0;
-            double dsum = 0.0;
-            for (uint32_t h0 = 0; h0 <= (vmax >> 1); h0 += 32) {
-                const uint32_t h = h0 + lane;
-                const uint32_t cnt = (s_bins[h >> 1] >> ((h & 1u) * 16)) & 0xffffu;
-                __syncwarp();
-                if ((lane & 1) == 0) s_bins[h >> 1] = 0;
-                uint32_t incl = cnt;
+            // warp 0: statistics from the counters (cleared on the way); the next unit's first counter update is
+            // two CTA barriers away
+            stats_from_counters(s_bins, s_vmax, nq, lane, prm.max_sq + unit, prm.p95_sq + unit * 2, prm.sum_dist + unit);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ column-sorted search
+// Default search.  One CTA per (item, class, direction).  The source contour is counting-sorted by its doubled
+// lattice column x2 into shared memory (int4 {y, x, y^2 + x^2, -}; col[c] .. col[c + 1] delimit column c).  A
+// warp owns 32 consecutive query vertices spanning the columns [x0, x1]:
+//   1. all lanes scan the sources of the columns [x0, x1] together (one broadcast LDS.128 per source vertex,
+//      2 IMAD + half a 3-input minimum per lane and vertex);
+//   2. r = isqrt(max over lanes of the best squared distance - 1) bounds every lane's remaining search: a
+//      nearer vertex lies less than sqrt(best) columns from the query, hence within [x0 - r, x1 + r].  The two
+//      flanks are scanned the same way.
+// The minimum is exact (every vertex that can beat a lane's best lies in the scanned columns; scanning a few
+// vertices more never hurts: loops run in steps of four over the sorted array, which is padded with copies
+// of a real vertex).  No boxes, no per-candidate tests: ~40 vertex evaluations per query on layered B-scans
+// against ~70 for the tiled search, and the worst case (contours far apart) is a brute-force scan.
+constexpr int kColThreads = 256;
+#ifndef OCTM_COL_MINB
+#define OCTM_COL_MINB 5
+#endif
+
+struct ColumnParams {
+    const uint32_t* verts;   // [n][K][2][max_pts]
+    const uint32_t* n_pts;   // [n][K][2]
+    long long n_units;       // n * K * 2
+    int max_pts;
+    int ncol;                // doubled-lattice columns: x2 < ncol (2 W)
+    uint32_t* d2;            // [n][K][2][max_pts]
+    uint32_t* max_sq;        // [n][K][2]      kNeedsSelect when the unit is left to distance_select_kernel
+    uint32_t* p95_sq;        // [n][K][2][2]
+    double* sum_dist;        // [n][K][2]
+    bool keep_d2;
+};
+
+__device__ __forceinline__ void coop_scan_range(const int4* src, int a, int b, int cy, int cx, int& bm) {
+#pragma unroll 1
+    for (int i = a; i < b; i += 4) {
+        const int4 s0 = src[i], s1 = src[i + 1], s2 = src[i + 2], s3 = src[i + 3];
+        const int m01 = min(s0.y * cx + (s0.x * cy + s0.z), s1.y * cx + (s1.x * cy + s1.z));
+        const int m23 = min(s2.y * cx + (s2.x * cy + s2.z), s3.y * cx + (s3.x * cy + s3.z));
+        bm = min(bm, min(m01, m23));
+    }
+}
+
+__global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_kernel(const ColumnParams prm) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ int s_next;
+    __shared__ uint32_t s_bins[kCountBins / 2];
+    __shared__ uint32_t s_vmax, s_big;
+    __shared__ uint32_t s_wtot[kColThreads / 32];
+    const int cap = prm.max_pts, ncol = prm.ncol;
+    int4* const src = reinterpret_cast<int4*>(dsm);                                                 // cap + 4 entries
+    uint32_t* const col = reinterpret_cast<uint32_t*>(dsm + (static_cast<size_t>(cap) + 4) * 16);   // ncol + 1 entries
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kColThreads / 32;
+    const int per = (ncol + kColThreads - 1) / kColThreads;      // columns per lane in the prefix sum
+    for (int i = threadIdx.x; i < kCountBins / 2; i += kColThreads) s_bins[i] = 0;
+
+    for (long long unit = blockIdx.x; unit < prm.n_units; unit += gridDim.x) {
+        const long long pair = unit >> 1;
+        const int dir = static_cast<int>(unit & 1);
+        // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
+        const int ns = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
+        const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
+        if (ns == 0 || nq == 0) {
+            if (threadIdx.x == 0) {
+                prm.max_sq[unit] = 0;
+                prm.p95_sq[unit * 2] = prm.p95_sq[unit * 2 + 1] = 0;
+                prm.sum_dist[unit] = 0.0;
+            }
+            continue;
+        }
+        const uint32_t* vs = prm.verts + (pair * 2 + dir) * static_cast<long long>(cap);
+        const uint32_t* vq = prm.verts + (pair * 2 + 1 - dir) * static_cast<long long>(cap);
+        uint32_t* dq = prm.d2 + unit * static_cast<long long>(cap);
+        const int nchunks = (nq + 31) >> 5;
+        {   // pull the next unit's vertex lists towards L2 while this one is searched
+            const long long nu = unit + gridDim.x;
+            if (nu < prm.n_units) {
+                const char* nv = reinterpret_cast<const char*>(prm.verts + (nu >> 1) * 2 * static_cast<long long>(cap));
+                const int lines = (2 * cap * 4 + 127) / 128;
+                for (int i = threadIdx.x; i < lines; i += kColThreads)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nv + static_cast<long long>(i) * 128));
+                if (threadIdx.x == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.n_pts + (nu >> 1) * 2));
+            }
+        }
+        __syncthreads();                               // every warp is done with the previous unit's tables
+        for (int i = threadIdx.x; i <= ncol; i += kColThreads) col[i] = 0;
+        if (threadIdx.x == 0) { s_next = 0; s_vmax = 0; s_big = 0; }
+        __syncthreads();
+        // counting sort by column: count into col[x + 1] ...
+        for (int i = threadIdx.x; i < ns; i += kColThreads) {
+            const int x = min(static_cast<int>(vs[i] & 0xffffu), ncol - 1);
+            atomicAdd(&col[x + 1], 1u);
+        }
+        __syncthreads();
+        // ... exclusive prefix sum in place (col[x + 1] = first slot of column x): every warp scans a contiguous
+        // block of 32 * per columns, then adds the totals of the warps before it ...
+        {
+            const int base = 1 + warp * 32 * per;
+            uint32_t carry = 0;
+            for (int k = 0; k < per; ++k) {
+                const int i = base + k * 32 + lane;
+                const uint32_t c = i <= ncol ? col[i] : 0u;
+                uint32_t incl = c;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += up;
                 }
-                const uint32_t first = base + incl - cnt;                    // ranks [first, first + cnt) hold value 2 h
-                const uint32_t m_lo = __ballot_sync(0xffffffffu, cnt != 0 && first <= lo && lo < first + cnt);
-                const uint32_t m_hi = __ballot_sync(0xffffffffu, cnt != 0 && first <= hi && hi < first + cnt);
-                if (m_lo) v_lo = 2 * (h0 + __ffs(m_lo) - 1);
-                if (m_hi) v_hi = 2 * (h0 + __ffs(m_hi) - 1);
-                if (cnt) dsum = __dadd_rn(dsum, __dmul_rn(static_cast<double>(cnt), sqrt(static_cast<double>(2 * h) / 4.0)));
-                base += __shfl_sync(0xffffffffu, incl, 31);
+                if (i <= ncol) col[i] = carry + incl - c;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dsum = __dadd_rn(dsum, __shfl_xor_sync(0xffffffffu, dsum, o));
-            if (lane == 0) {
-                prm.max_sq[unit] = vmax;
-                prm.p95_sq[unit * 2 + 0] = v_lo;
-                prm.p95_sq[unit * 2 + 1] = v_hi;
-                prm.sum_dist[unit] = dsum;
-            }
+            if (lane == 0) s_wtot[warp] = carry;
+            __syncthreads();
+            uint32_t off = 0;
+            for (int w = 0; w < warp; ++w) off += s_wtot[w];
+            if (off)
+                for (int k = 0; k < per; ++k) {
+                    const int i = base + k * 32 + lane;
+                    if (i <= ncol) col[i] += off;
+                }
         }
+        __syncthreads();
+        // ... and scatter: afterwards col[x + 1] is the END of column x, so column x is col[x] .. col[x + 1]
+        for (int i = threadIdx.x; i < ns; i += kColThreads) {
+            const uint32_t v = vs[i];
+            const int y = v >> 16, x = v & 0xffff;
+            const uint32_t slot = atomicAdd(&col[min(x, ncol - 1) + 1], 1u);
+            src[slot] = make_int4(y, x, y * y + x * x, 0);
+            if (i < 3) src[ns + i] = make_int4(y, x, y * y + x * x, 0);      // padding for the 4-wide scans
+        }
+        if (threadIdx.x < 3 && threadIdx.x >= ns) {                          // fewer than three vertices
+            const uint32_t v = vs[0];
+            const int y = v >> 16, x = v & 0xffff;
+            src[ns + threadIdx.x] = make_int4(y, x, y * y + x * x, 0);
+        }
+        __syncthreads();
+
+        // The final minima are counted (16-bit counters, one per even value) instead of stored; a unit with a value
+        // the counters cannot hold repeats the search in store mode and is left to distance_select_kernel.
+        bool count = nq <= 0xffff;
+        for (;;) {
+            for (;;) {                                 // chunks are handed out dynamically (shared counter)
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_next, 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= nchunks) break;
+                const int j = c * 32 + lane;
+                const uint32_t v = vq[min(j, nq - 1)];          // tail lanes repeat the last query
+                const int qy = v >> 16, qx = v & 0xffff;
+                const int cy = -2 * qy, cx = -2 * qx, qn = qy * qy + qx * qx;
+                const int x0 = min(__reduce_min_sync(0xffffffffu, qx), ncol - 1), x1 = min(__reduce_max_sync(0xffffffffu, qx), ncol - 1);
+                const int lo = static_cast<int>(col[x0]), hi = static_cast<int>(col[x1 + 1]);
+                int bm = 0x3fffffff;                   // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
+                coop_scan_range(src, lo, hi, cy, cx, bm);
+                const int bmax = __reduce_max_sync(0xffffffffu, bm + qn);
+                // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
+                const int r = bmax >= 0x3fffffff ? ncol          // nothing scanned yet (real distances are below 2^29)
+                                                 : static_cast<int>(sqrtf(static_cast<float>(bmax))) + (bmax >= (1 << 24) ? 1 : 0);
+                const int fl = static_cast<int>(col[max(x0 - r, 0)]), fr = static_cast<int>(col[min(x1 + r, ncol - 1) + 1]);
+                coop_scan_range(src, fl, lo, cy, cx, bm);
+                coop_scan_range(src, hi, fr, cy, cx, bm);
+                const int bestd = bm + qn;
+                if ((!count || prm.keep_d2) && j < nq) dq[j] = static_cast<uint32_t>(bestd);
+                if (!count) continue;
+                count_minima(bestd, j < nq, lane, s_bins, &s_vmax, &s_big);
+            }
+            if (!count) break;
+            __syncthreads();                           // counters, s_vmax, s_big complete
+            if (s_big == 0) break;
+            count = false;                             // CTA-uniform: search again, storing
+            if (threadIdx.x == 0) s_next = 0;
+            __syncthreads();
+        }
+        if (warp != 0) continue;
+        if (!count) {                                  // stored: hand the unit to the select kernel
+            if (lane == 0) prm.max_sq[unit] = kNeedsSelect;
+            if (nq <= 0xffff)
+                for (int i = lane; i < kCountBins / 2; i += 32) s_bins[i] = 0;
+            continue;
+        }
+        stats_from_counters(s_bins, s_vmax, nq, lane, prm.max_sq + unit, prm.p95_sq + unit * 2, prm.sum_dist + unit);
     }
 }
 
@@ -915,21 +1113,52 @@ static size_t dist_smem(int max_pts) {
 }
 
 extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
-                                       int max_pts, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
+                                       int max_pts, int H, int W, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
                                        uint32_t* d2, int keep_d2, void* stream) {
     if (n_items < 0 || num_classes < 1 || max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "bad shape");
+    if (H < 1 || W < 1 || H > 8192 || W > 8192) return octm::fail(OCTM_ERR_INVALID, "H, W outside [1, 8192]");
     if (n_items == 0) return OCTM_OK;
     if (!verts || !n_pts || !max_sq || !p95_sq || !sum_dist) return octm::fail(OCTM_ERR_INVALID, "null pointer");
-    // OCTM_DISTANCE_MODE = tiled (default: search kernel + select kernel) | lane (per-lane pruned search,
-    // one kernel) | brute (no pruning, one kernel); all three produce identical integers (tests run each).
-    static const int mode = [] {
+    // OCTM_DISTANCE_MODE = column (default: column-sorted cooperative search, falls back to tiled when the sorted
+    // contour does not fit shared memory) | tiled (cooperative box search) | lane (per-lane pruned search) |
+    // brute (no pruning); all produce identical integers (tests run each).
+    static const int env_mode = [] {
         const char* e = getenv("OCTM_DISTANCE_MODE");
         if (e && !strcmp(e, "brute")) return 2;
         if (e && !strcmp(e, "lane")) return 1;
-        return 0;
+        if (e && !strcmp(e, "tiled")) return 0;
+        return 3;
     }();
+    int mode = env_mode;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long n_pairs = n_items * num_classes;
+    auto run_select = [&]() -> int {
+        octm::SelectParams kp{n_pts, d2, n_pairs * 2, max_pts, max_sq, p95_sq, sum_dist};
+        long long kgrid = (n_pairs * 2 + 3) / 4;
+        const long long kcap = static_cast<long long>(octm::sm_count()) * 16;
+        if (kgrid > kcap) kgrid = kcap;
+        octm::distance_select_kernel<<<static_cast<unsigned>(kgrid), 128, 0, st>>>(kp);
+        return octm::check_launch("distance_select_kernel");
+    };
+    if (mode == 3) {
+        if (d2 == nullptr) return octm::fail(OCTM_ERR_INVALID, "d2 scratch [n][K][2][max_pts] is required");
+        const int ncol = 2 * W;
+        const size_t smem = (static_cast<size_t>(max_pts) + 4) * 16 + (static_cast<size_t>(ncol) + 1) * 4;
+        if (smem + 4096 > static_cast<size_t>(octm::max_optin_smem())) {
+            mode = 0;                                   // long contours: tile the source instead
+        } else {
+            if (cudaFuncSetAttribute(octm::distance_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)) != cudaSuccess)
+                return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_column_kernel) failed");
+            octm::ColumnParams cp{verts, n_pts, n_pairs * 2, max_pts, ncol, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0};
+            long long grid = n_pairs * 2;
+            const long long cap = static_cast<long long>(octm::sm_count()) * 32;
+            if (grid > cap) grid = cap;
+            octm::distance_column_kernel<<<static_cast<unsigned>(grid), octm::kColThreads, smem, st>>>(cp);
+            if (int e = octm::check_launch("distance_column_kernel")) return e;
+            return run_select();
+        }
+    }
     if (mode == 0) {
         if (d2 == nullptr) return octm::fail(OCTM_ERR_INVALID, "d2 scratch [n][K][2][max_pts] is required");
         static const int env_tile = [] { const char* e = getenv("OCTM_DIST_TILE"); return e ? atoi(e) : 0; }();
@@ -947,12 +1176,7 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
         if (grid > cap) grid = cap;
         octm::distance_search_kernel<<<static_cast<unsigned>(grid), octm::kSearchThreads, smem, st>>>(sp);
         if (int e = octm::check_launch("distance_search_kernel")) return e;
-        octm::SelectParams kp{n_pts, d2, n_pairs * 2, max_pts, max_sq, p95_sq, sum_dist};
-        long long kgrid = (n_pairs * 2 + 3) / 4;
-        const long long kcap = static_cast<long long>(octm::sm_count()) * 16;
-        if (kgrid > kcap) kgrid = kcap;
-        octm::distance_select_kernel<<<static_cast<unsigned>(kgrid), 128, 0, st>>>(kp);
-        return octm::check_launch("distance_select_kernel");
+        return run_select();
     }
     const size_t smem = dist_smem(max_pts);
     if (smem > static_cast<size_t>(octm::max_optin_smem()) - 4096)
@@ -1005,5 +1229,5 @@ extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
     if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, max_pts, verts, n_pts,
                                         flags, stream))
         return e;
-    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, max_sq, p95_sq, sum_dist, d2_ws, 0, stream);
+    return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2_ws, 0, stream);
 }

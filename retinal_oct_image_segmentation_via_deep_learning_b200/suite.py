@@ -245,7 +245,7 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
         _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), max_pts, _ptr(verts),
                   _ptr(n_pts), _ptr(flags), _stream())
     with _Timed(timers, "contour_distance"):
-        _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, _ptr(max_sq), _ptr(p95),
+        _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, h, w, _ptr(max_sq), _ptr(p95),
                   _ptr(sums), _ptr(sq), 1 if want_sq else 0, _stream())
     return ContourOut(n_pts, flags, max_sq, p95, sums, verts if want_verts else None, sq if want_sq else None, max_pts)
 

@@ -1,4 +1,4 @@
-"""GPU parity: the distance-search strategies (tiled cooperative boxes + select kernel, per-lane boxes,
+"""GPU parity: the distance-search strategies (column-sorted, tiled cooperative boxes, per-lane boxes,
 brute force) return identical squared distances -- pruning and tiling never change a result."""
 import json
 import os
@@ -47,6 +47,7 @@ def _run(mode, tile=None):
 
 def test_all_modes_agree(cuda):
     ref = _run("brute")
+    assert _run("column") == ref                # default: column-sorted cooperative search
     assert _run("tiled") == ref
     assert _run("tiled", tile=64) == ref        # contours span many source tiles
     assert _run("lane") == ref
