@@ -534,15 +534,21 @@ constexpr uint32_t kNeedsSelect = 0xffffffffu;      // not a squared distance (c
 // Counting form of the per-unit statistics (shared by both search kernels).  Squared distances between contour
 // vertices are even (a vertex has exactly one odd doubled-lattice coordinate), so value 2 h is counted in 16-bit
 // counter h, two counters per word.  Equal values of a warp are merged with MATCH.ANY: one shared-memory atomic
-// per distinct value.  A value the counters cannot hold raises *s_big.
-__device__ __forceinline__ void count_minima(int bestd, bool valid, int lane, uint32_t* s_bins, uint32_t* s_vmax,
-                                             uint32_t* s_big) {
+// per distinct value.  The running maximum and a flag for values the counters cannot hold stay in registers.
+__device__ __forceinline__ void count_minima(int bestd, bool valid, int lane, uint32_t* s_bins, uint32_t& run_max,
+                                             bool& run_bad) {
     const uint32_t dv = static_cast<uint32_t>(bestd), h = dv >> 1;
     const bool ok = valid && (dv & 1u) == 0 && h < static_cast<uint32_t>(kCountBins);
     const uint32_t peers = __match_any_sync(0xffffffffu, ok ? h : static_cast<uint32_t>(kCountBins) + lane);
     if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_bins[h >> 1], static_cast<uint32_t>(__popc(peers)) << ((h & 1u) * 16));
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, valid ? dv : 0u);
-    const bool bad = __any_sync(0xffffffffu, valid && !ok);
+    if (valid) run_max = max(run_max, dv);
+    run_bad |= valid && !ok;
+}
+
+// A warp publishes what count_minima gathered over its chunks (before the CTA barrier that completes the counters).
+__device__ __forceinline__ void publish_counts(uint32_t run_max, bool run_bad, int lane, uint32_t* s_vmax, uint32_t* s_big) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, run_max);
+    const bool bad = __any_sync(0xffffffffu, run_bad);
     if (lane == 0) {
         atomicMax(s_vmax, wmax);
         if (bad) *s_big = 1;
@@ -672,6 +678,8 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
             // hold repeats the tile's search in store mode and is left to distance_select_kernel.
             const bool last = t0 + tile >= ns_all;
             bool count = last && nq <= 0xffff;
+            uint32_t run_max = 0;
+            bool run_bad = false;
           for (;;) {
             // chunks are handed out dynamically (shared counter): their cost varies with the local geometry
             for (;;) {
@@ -722,9 +730,10 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
                 }
                 if ((!count || prm.keep_d2) && j < nq) dq[j] = static_cast<uint32_t>(bestd);
                 if (!count) continue;
-                count_minima(bestd, j < nq, lane, s_bins, &s_vmax, &s_big);
+                count_minima(bestd, j < nq, lane, s_bins, run_max, run_bad);
             }
             if (!count) break;
+            publish_counts(run_max, run_bad, lane, &s_vmax, &s_big);
             __syncthreads();                       // counters, s_vmax, s_big complete
             if (s_big == 0) break;
             count = false;                         // CTA-uniform: search the tile again, storing
@@ -789,7 +798,6 @@ __device__ __forceinline__ void coop_scan_range(const int4* src, int a, int b, i
 
 __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_kernel(const ColumnParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
-    __shared__ int s_next;
     __shared__ uint32_t s_bins[kCountBins / 2];
     __shared__ uint32_t s_vmax, s_big;
     __shared__ uint32_t s_wtot[kColThreads / 32];
@@ -800,6 +808,7 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
     constexpr int kWarps = kColThreads / 32;
     const int per = (ncol + kColThreads - 1) / kColThreads;      // columns per lane in the prefix sum
     for (int i = threadIdx.x; i < kCountBins / 2; i += kColThreads) s_bins[i] = 0;
+    bool synced = false;                               // CTA-uniform: the previous unit ended with a CTA barrier
 
     for (long long unit = blockIdx.x; unit < prm.n_units; unit += gridDim.x) {
         const long long pair = unit >> 1;
@@ -829,9 +838,9 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
                 if (threadIdx.x == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.n_pts + (nu >> 1) * 2));
             }
         }
-        __syncthreads();                               // every warp is done with the previous unit's tables
+        if (!synced) __syncthreads();                  // every warp is done with the previous unit's tables
         for (int i = threadIdx.x; i <= ncol; i += kColThreads) col[i] = 0;
-        if (threadIdx.x == 0) { s_next = 0; s_vmax = 0; s_big = 0; }
+        if (threadIdx.x == 0) { s_vmax = 0; s_big = 0; }
         __syncthreads();
         // counting sort by column: count into col[x + 1] ...
         for (int i = threadIdx.x; i < ns; i += kColThreads) {
@@ -885,39 +894,51 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
         // The final minima are counted (16-bit counters, one per even value) instead of stored; a unit with a value
         // the counters cannot hold repeats the search in store mode and is left to distance_select_kernel.
         bool count = nq <= 0xffff;
+        uint32_t run_max = 0;
+        bool run_bad = false;
         for (;;) {
-            for (;;) {                                 // chunks are handed out dynamically (shared counter)
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_next, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c >= nchunks) break;
+#pragma unroll 1
+            for (int c = warp; c < nchunks; c += kWarps) {
                 const int j = c * 32 + lane;
                 const uint32_t v = vq[min(j, nq - 1)];          // tail lanes repeat the last query
                 const int qy = v >> 16, qx = v & 0xffff;
                 const int cy = -2 * qy, cx = -2 * qx, qn = qy * qy + qx * qx;
-                const int x0 = min(__reduce_min_sync(0xffffffffu, qx), ncol - 1), x1 = min(__reduce_max_sync(0xffffffffu, qx), ncol - 1);
-                const int lo = static_cast<int>(col[x0]), hi = static_cast<int>(col[x1 + 1]);
+                // Consecutive polyline vertices are at most 2 columns apart; a larger step is the seam between the
+                // forward and the backward run of an open contour (or the closing repeat): the queries before and
+                // after it get their own column span, so that no span covers the columns in between.
+                const int qprev = __shfl_up_sync(0xffffffffu, qx, 1);
+                const uint32_t seam = __ballot_sync(0xffffffffu, lane > 0 && abs(qx - qprev) > 2);
+                uint32_t part = seam ? (1u << (__ffs(seam) - 1)) - 1u : 0xffffffffu;
                 int bm = 0x3fffffff;                   // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
-                coop_scan_range(src, lo, hi, cy, cx, bm);
-                const int bmax = __reduce_max_sync(0xffffffffu, bm + qn);
-                // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
-                const int r = bmax >= 0x3fffffff ? ncol          // nothing scanned yet (real distances are below 2^29)
-                                                 : static_cast<int>(sqrtf(static_cast<float>(bmax))) + (bmax >= (1 << 24) ? 1 : 0);
-                const int fl = static_cast<int>(col[max(x0 - r, 0)]), fr = static_cast<int>(col[min(x1 + r, ncol - 1) + 1]);
-                coop_scan_range(src, fl, lo, cy, cx, bm);
-                coop_scan_range(src, hi, fr, cy, cx, bm);
+                for (;;) {
+                    const bool mine = (part >> lane) & 1u;
+                    const int x0 = min(__reduce_min_sync(0xffffffffu, mine ? qx : 0x7fffffff), ncol - 1);
+                    const int x1 = min(__reduce_max_sync(0xffffffffu, mine ? qx : 0), ncol - 1);
+                    const int lo = static_cast<int>(col[x0]), hi = static_cast<int>(col[x1 + 1]);
+                    coop_scan_range(src, lo, hi, cy, cx, bm);
+                    const int bmax = __reduce_max_sync(0xffffffffu, mine ? bm + qn : 0);
+                    // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
+                    // (the approximate square root is exact enough below 2^20; real distances are below 2^29)
+                    float rf;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(static_cast<float>(bmax)));
+                    const int r = bmax >= 0x3fffffff ? ncol : static_cast<int>(rf) + (bmax >= (1 << 20) ? 1 : 0);
+                    const int fl = static_cast<int>(col[max(x0 - r, 0)]), fr = static_cast<int>(col[min(x1 + r, ncol - 1) + 1]);
+                    coop_scan_range(src, fl, lo, cy, cx, bm);
+                    coop_scan_range(src, hi, fr, cy, cx, bm);
+                    if (part == 0xffffffffu || (part & 1u) == 0) break;
+                    part = ~part;                      // the queries after the seam
+                }
                 const int bestd = bm + qn;
                 if ((!count || prm.keep_d2) && j < nq) dq[j] = static_cast<uint32_t>(bestd);
-                if (!count) continue;
-                count_minima(bestd, j < nq, lane, s_bins, &s_vmax, &s_big);
+                if (count) count_minima(bestd, j < nq, lane, s_bins, run_max, run_bad);
             }
             if (!count) break;
+            publish_counts(run_max, run_bad, lane, &s_vmax, &s_big);
             __syncthreads();                           // counters, s_vmax, s_big complete
             if (s_big == 0) break;
             count = false;                             // CTA-uniform: search again, storing
-            if (threadIdx.x == 0) s_next = 0;
-            __syncthreads();
         }
+        synced = count;                                // the barrier above also ends every warp's use of the tables
         if (warp != 0) continue;
         if (!count) {                                  // stored: hand the unit to the select kernel
             if (lane == 0) prm.max_sq[unit] = kNeedsSelect;
