@@ -278,6 +278,16 @@ def run_b200(args):
     if not args.no_e2e:
         m = min(n, args.e2e_items)
         ht, hp = yt[:m].cpu().pin_memory(), yp[:m].cpu().pin_memory()
+        # this box's pinned host->device copy rate: the ceiling of the end-to-end number (boxes differ by 2-3x)
+        probe_d = torch.empty_like(yt[:m])
+        probe_d.copy_(ht, non_blocking=True)
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
+        for _ in range(2):
+            probe_d.copy_(ht, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 2 * ht.numel() / (time.perf_counter() - tp) / 1e9
+        del probe_d
         for _ in range(max(1, min(args.warmup, 2))):
             suite.evaluate_host(ht, hp, K, contours=not args.no_contours, device=dev).metrics()
         barrier()
@@ -294,7 +304,9 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * m * e2e_steps / float(t.item()), "unit": "B-scans/s",
                "h2d_bytes_per_step": int(m * BYTES_PER_BSCAN), "d2h_bytes_per_step": int(d2h),
-               "items_per_step_per_gpu": m, "steps": e2e_steps}
+               "items_per_step_per_gpu": m, "steps": e2e_steps,
+               "pinned_h2d_gbs_this_box": round(h2d_gbs, 1),
+               "h2d_gbs_achieved": round(world * m * e2e_steps * BYTES_PER_BSCAN / float(t.item()) / 1e9 / world, 1)}
 
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None   # device-timed + e2e regions
     if rank == 0:

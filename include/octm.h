@@ -154,8 +154,12 @@ OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int
                       void* stream);
 
 /* The two stages of the above, exposed for tests and for callers that want the vertices.
- *   verts   uint32 [n][K][2][max_pts]  packed (y2 << 16 | x2) doubled-lattice vertices in trace
- *                                      order (the closing repeat, if any, is the last entry)
+ *   verts   uint32 [n][K][2][max_pts]  packed (y2 << 16 | x2) doubled-lattice vertices of contour [0]: the
+ *                                      polyline's vertices, each once, in an unspecified order except
+ *                                      that the closing repeat, if any, is the last entry.  With the
+ *                                      label pass's boundary rows (bnd_true / bnd_pred) layered maps
+ *                                      are not walked: their contours are verified and emitted in
+ *                                      parallel (left to right); without them every contour is walked.
  *   d2      uint32 [n][K][2][max_pts]  per-query-vertex D2: [i][c][d][j] = squared distance from vertex j
  *                                      of map 1-d to the nearest vertex of map d.  Required.  With
  *                                      keep_d2 == 0 it is scratch and its contents are unspecified on
@@ -164,7 +168,9 @@ OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int
 OCTM_API int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t item_elems, int num_classes,
                       uint32_t* first_pos /* [n][K] */, void* stream);
 OCTM_API int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H,
-                            int W, int num_classes, const uint32_t* first_pos, int max_pts,
+                            int W, int num_classes, const uint32_t* first_pos,
+                            const int32_t* bnd_true /* [n][K-1][W] from octm_label_pass_u8, or NULL */,
+                            const int32_t* bnd_pred, int max_pts,
                             uint32_t* verts, uint32_t* n_pts, uint32_t* flags, void* stream);
 OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items,
                             int num_classes, int max_pts, int H, int W /* shape the vertices were traced on */,

@@ -39,32 +39,46 @@ struct TraceParams {
     uint32_t* verts;             // [n][K][2][max_pts]
     uint32_t* n_pts;             // [n][K][2]
     uint32_t* flags;             // [n][K]
+    const int* bnd_t;            // [n][K-1][W] #{label < k} per column of y_true (label pass), or null
+    const int* bnd_p;
+    bool only_todo;              // walk only the contours trace_layered_kernel left (n_pts == kTraceTodo)
 };
 
-// 16 aligned label bytes from global memory unless the lane already holds them (`w` keeps its value when
-// tag == widx).  A predicated load, not a branch: lanes of a warp hit and miss independently.  On a miss the
-// same columns of the two rows above and below are prefetched into L2: the walk is latency-bound on exactly
-// these first touches (ncu: 72 % of its stall samples wait on the label loads, which miss L2).
-__device__ __forceinline__ void load_row16_if_new(uint4& w, uint32_t tag, uint32_t widx, const uint4* base, const uint4* up1,
-                                                  const uint4* dn1, const uint4* up2, const uint4* dn2) {
+constexpr uint32_t kTraceTodo = 0xffffffffu;
+
+// Both row caches of the walk in one go: 16 aligned label bytes for the even-row cache and 16 for the odd-row
+// cache, each loaded only when its predicate is set (lanes of a warp hit and miss independently: predicated
+// loads, not branches).  The two loads are issued back to back, so a step that needs both rows waits for one
+// memory latency, not two.  (Asking L2 for the line ahead in the direction of travel, or for the rows above
+// and below, was measured slower both times: the prefetches cost more LSU slots than the latency they hide.)
+__device__ __forceinline__ void load_rows16(uint4& re, uint4& ro, bool pe, bool po, const uint4* ae, const uint4* ao) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.u32 p, %4, %5;\n"
-        "@p ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%6];\n"
-#ifdef OCTM_TRACE_PREFETCH
-        "@p prefetch.global.L2 [%7];\n"
-        "@p prefetch.global.L2 [%8];\n"
-        "@p prefetch.global.L2 [%9];\n"
-        "@p prefetch.global.L2 [%10];\n"
-#endif
+        ".reg .pred pe, po;\n"
+        "setp.ne.u32 pe, %8, 0;\n"
+        "setp.ne.u32 po, %9, 0;\n"
+        "@pe ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%10];\n"
+        "@po ld.global.nc.L2::128B.v4.u32 {%4, %5, %6, %7}, [%11];\n"
         "}\n"
-        : "+r"(w.x), "+r"(w.y), "+r"(w.z), "+r"(w.w)
-        : "r"(tag), "r"(widx), "l"(base), "l"(up1), "l"(dn1), "l"(up2), "l"(dn2));
+        : "+r"(re.x), "+r"(re.y), "+r"(re.z), "+r"(re.w), "+r"(ro.x), "+r"(ro.y), "+r"(ro.z), "+r"(ro.w)
+        : "r"(static_cast<uint32_t>(pe)), "r"(static_cast<uint32_t>(po)), "l"(ae), "l"(ao));
+}
+
+// 16 aligned label bytes through the non-coherent path
+__device__ __forceinline__ uint4 ldg_labels16(const uint4* p) {
+    uint4 w;
+    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p));
+    return w;
+}
+
+// label byte (c & 15) of a 16-byte group
+__device__ __forceinline__ uint32_t label_of(const uint4& w, uint32_t c) {
+    const uint32_t lo = __byte_perm(w.x, w.y, c & 7u), hi = __byte_perm(w.z, w.w, c & 7u);
+    return ((c & 8u) ? hi : lo) & 0xffu;
 }
 
 // WORDS: W % 16 == 0 and 16-byte aligned maps -> the walk reads aligned 16-byte label groups and keeps the last
-// group of the even and of the odd row in registers.
+// group of the even and of the odd row in registers (load_rows16).
 #ifndef OCTM_TRACE_MINB
 #define OCTM_TRACE_MINB 8
 #endif
@@ -91,6 +105,7 @@ __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const Trace
     const uint8_t* L = (m ? prm.yp : prm.yt) + item * H * static_cast<long long>(W);
     uint32_t* out = prm.verts + ((item * K + cls) * 2 + m) * static_cast<long long>(prm.max_pts);
     const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
+    if (prm.only_todo && prm.n_pts[(item * K + cls) * 2 + m] != kTraceTodo) continue;
     uint32_t npts = 0;
     bool closed = false, overflow = false;
 
@@ -110,7 +125,7 @@ __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const Trace
         uint32_t g0 = 0, g1 = 0, g2 = 0;
         // register cache of the last aligned 16-byte label group of an even (0) and an odd (1) row
         const uint4* L16 = reinterpret_cast<const uint4*>(L);
-        const uint32_t w16 = static_cast<uint32_t>(W) >> 4, hmax = static_cast<uint32_t>(H - 1);
+        const uint32_t w16 = static_cast<uint32_t>(W) >> 4;
         uint32_t tag0 = 0xffffffffu, tag1 = 0xffffffffu;
         uint4 row0 = make_uint4(0, 0, 0, 0), row1 = row0;
         const uint32_t c4 = 0x01010101u * static_cast<uint32_t>(cls);
@@ -126,26 +141,27 @@ __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const Trace
             [&](int r0, int c0, int e) -> int {
                 // the two pixels not shared with the previous square (trace_core.h: carried_bits)
                 if (WORDS) {
+                    const bool horiz = e >= 2;
                     const uint32_t ra = r0 + (e == 1), ca = c0 + (e == 3);
-                    const uint32_t rb = ra + (e >= 2), cb = ca + (e < 2);
-                    int bits = 0;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint32_t r = k ? rb : ra, c = k ? cb : ca;
-                        const uint32_t widx = r * w16 + (c >> 4);
-                        const bool odd = r & 1u;
-                        uint4 w = odd ? row1 : row0;
-                        const uint32_t rm1 = r > 0 ? r - 1 : 0, rm2 = r > 1 ? r - 2 : 0;
-                        const uint32_t rp1 = min(r + 1, hmax), rp2 = min(r + 2, hmax);
-                        const uint4* col = L16 + (c >> 4);
-                        load_row16_if_new(w, odd ? tag1 : tag0, widx, L16 + widx, col + rm1 * w16, col + rp1 * w16,
-                                          col + rm2 * w16, col + rp2 * w16);
-                        tag0 = odd ? tag0 : widx; tag1 = odd ? widx : tag1;
-                        if (odd) row1 = w; else row0 = w;
-                        const uint32_t q = (c >> 2) & 3u;
-                        const uint32_t word = q < 2 ? (q == 0 ? w.x : w.y) : (q == 2 ? w.z : w.w);
-                        bits |= (((word >> ((c & 3u) * 8u)) & 0xffu) == static_cast<uint32_t>(cls) ? 1 : 0) << k;
+                    const uint32_t rb = ra + (horiz ? 1u : 0u), cb = ca + (horiz ? 0u : 1u);
+                    const uint32_t wa = ra * w16 + (ca >> 4);
+                    const uint32_t wb = horiz ? wa + w16 : ra * w16 + (cb >> 4);
+                    const bool oa = ra & 1u;
+                    // a horizontal move needs one pixel of an even and one of an odd row; a vertical move two
+                    // neighbours of one row (the second is in another group once in 16 moves: third load below)
+                    const uint32_t want0 = oa ? wb : wa, want1 = oa ? wa : wb;
+                    const bool p0 = (horiz || !oa) && tag0 != want0, p1 = (horiz || oa) && tag1 != want1;
+                    load_rows16(row0, row1, p0, p1, L16 + want0, L16 + want1);
+                    tag0 = p0 ? want0 : tag0;
+                    tag1 = p1 ? want1 : tag1;
+                    const uint32_t la = oa ? label_of(row1, ca) : label_of(row0, ca);
+                    if (!horiz && wb != wa) {                               // rare: the pair straddles two groups
+                        const uint4 w = __ldg(L16 + wb);
+                        if (oa) { row1 = w; tag1 = wb; } else { row0 = w; tag0 = wb; }
                     }
+                    const bool ob = rb & 1u;
+                    const uint32_t lb = ob ? label_of(row1, cb) : label_of(row0, cb);
+                    const int bits = (la == static_cast<uint32_t>(cls) ? 1 : 0) | (lb == static_cast<uint32_t>(cls) ? 2 : 0);
                     return bits;
                 }
                 const uint8_t* p = L + (static_cast<uint32_t>(r0) * static_cast<uint32_t>(W) + static_cast<uint32_t>(c0));
@@ -177,6 +193,111 @@ __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const Trace
     if (closed) f |= m ? OCTM_CF_PRED_CLOSED : OCTM_CF_TRUE_CLOSED;
     if (overflow) f |= m ? OCTM_CF_PRED_OVERFLOW : OCTM_CF_TRUE_OVERFLOW;
     if (f) atomicOr(&prm.flags[item * K + cls], f);
+    }
+}
+
+// ------------------------------------------------------------------------------ layered fast path
+// On a layered B-scan contour [0] of a class mask is the boundary between "mask as at pixel (0, 0)" above and
+// the rest below, running from the left to the right image border: a height function h(x).  The label pass
+// already knows a candidate: h(x) = #{label < k} in column x (its boundary rows).  This kernel checks the
+// candidate instead of walking it: one WARP per (item, class, map), 32 adjacent columns at a time, a lane each:
+//   * 1 <= h(x) <= H - 1 everywhere;
+//   * every pixel of every 2x2 square the walk would visit has the value the step function predicts: in column
+//     x the rows [min(h(x-1), h(x), h(x+1)) - 1, max(..)] hold "mask(0,0)" above h(x) and the opposite from h(x)
+//     down (byte loads, adjacent lanes = adjacent columns, four rows in flight);
+//   * the raster-first pixel of the path is the seed the label pass found (no pixel of the class above it).
+// The walk is a deterministic function of exactly these pixels and starts at the seed's square, so when all
+// three hold it would trace this very polyline.  Its vertices -- (2 h(x) - 1, 2 x) per column and (2 r, 2 x + 1)
+// for the rows r between h(x) and h(x+1) -- are written straight to the vertex list, left to right, at
+// positions from a warp prefix sum (adjacent lanes write adjacent words).  Everything else (blobs, broken or
+// touching layers, too many vertices) gets n_pts = kTraceTodo and is walked by trace_kernel afterwards, which
+// overwrites whatever part of the list was written before the check failed.
+#ifndef OCTM_LAYERED_MINB
+#define OCTM_LAYERED_MINB 8
+#endif
+__global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(const TraceParams prm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = prm.K, H = prm.H, W = prm.W;
+    const uint32_t cap = static_cast<uint32_t>(prm.max_pts);
+    const long long total = prm.n_items * K * 2, per_map = prm.n_items * K;
+    for (long long gid = static_cast<long long>(blockIdx.x) * 4 + warp; gid < total; gid += static_cast<long long>(gridDim.x) * 4) {
+        const int m = gid >= per_map ? 1 : 0;
+        const long long rem = gid - m * per_map;
+        const long long item = rem / K;
+        const int cls = static_cast<int>(rem % K);
+        const uint8_t* L = (m ? prm.yp : prm.yt) + item * H * static_cast<long long>(W);
+        uint32_t* out = prm.verts + ((item * K + cls) * 2 + m) * static_cast<long long>(cap);
+        uint32_t* np = prm.n_pts + (item * K + cls) * 2 + m;
+        const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
+        // one load for all seeds; the class at pixel (0, 0) is the one whose first occurrence is index 0
+        const uint32_t myfp = lane < K ? fp[lane] : OCTM_NO_SEED;
+        const int c00 = __ffs(__ballot_sync(0xffffffffu, myfp == 0u)) - 1;
+        const bool inv = cls == c00;                       // the class is the region above the path
+        const uint32_t others = __reduce_min_sync(0xffffffffu, lane == c00 ? OCTM_NO_SEED : myfp);
+        const uint32_t seed = inv ? others : __shfl_sync(0xffffffffu, myfp, cls);
+        if (seed == OCTM_NO_SEED) {                        // empty or full mask: no contour
+            if (lane == 0) *np = 0;
+            continue;
+        }
+        const int brow = inv ? cls : cls - 1;              // h = #{label < brow + 1}
+        bool ok = brow >= 0 && brow < K - 1;
+        const int* hrow = (m ? prm.bnd_p : prm.bnd_t) + (item * (K - 1) + (ok ? brow : 0)) * static_cast<long long>(W);
+        uint32_t base = 0, minkey = 0xffffffffu;
+        bool bad = false;
+        int hleft = 0;                                     // h of the column left of this block
+        int hcur = ok ? hrow[min(lane, W - 1)] : 1;
+        for (int x0 = 0; ok && x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            const bool valid = x < W;
+            const int xc = min(x, W - 1);
+            const int h = hcur;
+            hcur = hrow[min(x + 32, W - 1)];               // next block's heights, in flight during this block's checks
+            int hl = __shfl_up_sync(0xffffffffu, h, 1);
+            if (lane == 0) hl = x0 > 0 ? hleft : h;
+            int hr = __shfl_down_sync(0xffffffffu, h, 1);
+            const int hfirst_next = __shfl_sync(0xffffffffu, hcur, 0);
+            if (lane == 31) hr = hfirst_next;
+            if (x + 1 >= W) hr = h;
+            hleft = __shfl_sync(0xffffffffu, h, 31);
+            if (!__all_sync(0xffffffffu, !valid || static_cast<unsigned>(h - 1) <= static_cast<unsigned>(H - 2))) { ok = false; break; }
+            const int lo = min(hl, min(h, hr)) - 1, hi = max(hl, max(h, hr));
+            // rows as 32-bit offsets from the column's first pixel (H * W < 2^31 on this path)
+            const uint8_t* colp = L + xc;
+            const int olo = lo * W, ohi = hi * W, oh = h * W;
+            const int nrows = __reduce_max_sync(0xffffffffu, valid ? hi - lo + 1 : 0);
+            for (int u0 = 0; u0 < nrows; u0 += 4) {        // four rows in flight
+                int off[4];
+                uint32_t px[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {              // past the window: its last row again (harmless)
+                    off[u] = min(olo + (u0 + u) * W, ohi);
+                    px[u] = __ldg(colp + off[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bad |= ((px[u] == static_cast<uint32_t>(cls)) != (off[u] >= oh)) != inv;
+            }
+            // vertices of these columns at their left-to-right positions
+            const int dh = abs(hr - h);
+            const uint32_t cnt = valid ? 1u + static_cast<uint32_t>(dh) : 0u;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const uint32_t pos = base + incl - cnt;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+            if (base > cap) { ok = false; break; }         // too long: the walk flags the overflow
+            if (valid) {
+                const uint32_t x2 = 2u * static_cast<uint32_t>(x);
+                minkey = min(minkey, static_cast<uint32_t>(h) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x));
+                out[pos] = (static_cast<uint32_t>(2 * h - 1) << 16) | x2;
+                const int ra = min(h, hr);
+                for (int t = 0; t < dh; ++t) out[pos + 1 + t] = (static_cast<uint32_t>(2 * (ra + t)) << 16) | (x2 + 1u);
+            }
+        }
+        if (ok) ok = !__any_sync(0xffffffffu, bad) && __reduce_min_sync(0xffffffffu, minkey) == seed;
+        if (lane == 0) *np = ok ? base : kTraceTodo;
     }
 }
 
@@ -1100,20 +1221,38 @@ extern "C" int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t
 }
 
 extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
-                                       int num_classes, const uint32_t* first_pos, int max_pts, uint32_t* verts,
-                                       uint32_t* n_pts, uint32_t* flags, void* stream) {
+                                       int num_classes, const uint32_t* first_pos, const int32_t* bnd_true,
+                                       const int32_t* bnd_pred, int max_pts, uint32_t* verts, uint32_t* n_pts,
+                                       uint32_t* flags, void* stream) {
     if (int e = check_shape(n_items, H, W, num_classes, max_pts)) return e;
     if (n_items == 0) return OCTM_OK;
     if (!y_true || !y_pred || !first_pos || !verts || !n_pts || !flags) return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    if ((bnd_true == nullptr) != (bnd_pred == nullptr)) return octm::fail(OCTM_ERR_INVALID, "bnd_true/bnd_pred: both or neither");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n_items * num_classes, s) != cudaSuccess)
         return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
-    octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags};
+    octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags,
+                        bnd_true, bnd_pred, false};
+    const bool words = W % 16 == 0 && reinterpret_cast<uintptr_t>(y_true) % 16 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 16 == 0;
     const long long threads = n_items * num_classes * 2;
+    // layered fast path (needs the label pass's boundary rows): OCTM_TRACE_LAYERED=0 turns it off
+    static const bool env_layered = [] { const char* e = getenv("OCTM_TRACE_LAYERED"); return !(e && e[0] == '0'); }();
+    if (env_layered && bnd_true != nullptr && H >= 2 && num_classes >= 2 && num_classes <= 32) {
+        int fit = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_layered_kernel, 128, 0) != cudaSuccess || fit < 1) {
+            cudaGetLastError();
+            fit = 8;
+        }
+        long long grid = (threads + 3) / 4;
+        const long long cap = static_cast<long long>(octm::sm_count()) * fit;
+        if (grid > cap) grid = cap;
+        octm::trace_layered_kernel<<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
+        if (int e = octm::check_launch("trace_layered_kernel")) return e;
+        p.only_todo = true;
+    }
     static const int env_ctas = [] { const char* e = getenv("OCTM_TRACE_CTAS"); return e ? atoi(e) : 0; }();
-    const bool words_probe = W % 16 == 0;
     int fit = 0;       // persistent grid: every CTA that can be resident (the walk is latency-bound: occupancy hides it)
-    if ((words_probe ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<true>, 128, 0)
+    if ((W % 16 == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<true>, 128, 0)
                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<false>, 128, 0)) != cudaSuccess || fit < 1) {
         cudaGetLastError();
         fit = 8;
@@ -1122,7 +1261,6 @@ extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_p
     long long grid = (threads + 127) / 128;
     const long long cap = static_cast<long long>(octm::sm_count()) * ctas_per_sm;
     if (grid > cap) grid = cap;
-    const bool words = W % 16 == 0 && reinterpret_cast<uintptr_t>(y_true) % 16 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 16 == 0;
     if (words) octm::trace_kernel<true><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
     else octm::trace_kernel<false><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
     return octm::check_launch("trace_kernel");
@@ -1247,7 +1385,7 @@ extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
         if (int e = octm::check_launch("first_pos_kernel")) return e;
         first_pos = fp_ws;
     }
-    if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, max_pts, verts, n_pts,
+    if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, nullptr, nullptr, max_pts, verts, n_pts,
                                         flags, stream))
         return e;
     return octm_contour2d_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2_ws, 0, stream);

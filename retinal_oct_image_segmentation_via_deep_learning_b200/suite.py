@@ -226,7 +226,7 @@ def _vertex_scratch(dev, numel):
     return buf[:numel]
 
 
-def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None):
+def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None, bnd=None):
     n, h, w = yt.shape
     max_pts = (int(max_pts) + 3) & ~3          # vertices are stored in 16-byte groups
     dev = yt.device
@@ -242,7 +242,8 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
     p95 = torch.empty((n, k, 2, 2), **i32)
     sums = torch.empty((n, k, 2), dtype=torch.float64, device=dev)
     with _Timed(timers, "contour_trace"):
-        _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), max_pts, _ptr(verts),
+        _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos),
+                  _ptr(bnd[0]) if bnd else None, _ptr(bnd[1]) if bnd else None, max_pts, _ptr(verts),
                   _ptr(n_pts), _ptr(flags), _stream())
     with _Timed(timers, "contour_distance"):
         _lib.call("octm_contour2d_distance", _ptr(verts), _ptr(n_pts), n, k, max_pts, h, w, _ptr(max_sq), _ptr(p95),
@@ -251,8 +252,11 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
 
 
 def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
-                 return_sq=False, timers=None, check_overflow=True):
+                 return_sq=False, timers=None, check_overflow=True, boundaries=None):
     """Contour ``[0]`` of every class mask of both maps, then hausdorff / hd95 / assd integers.
+
+    ``boundaries``: optional ``(bnd_true, bnd_pred)`` int32 ``[N, K-1, W]`` of the label pass; with them the
+    contours of layered maps are verified and emitted in parallel instead of walked (same vertices).
 
     Items are processed in chunks so the vertex workspace stays under ~1 GiB; items whose contour is
     longer than ``max_pts`` are re-run on their own with a larger bound."""
@@ -276,7 +280,8 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
         parts = []
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            parts.append(_contour_chunk(yt[s:e], yp[s:e], k, first_pos[s:e], max_pts, return_vertices, return_sq, timers))
+            parts.append(_contour_chunk(yt[s:e], yp[s:e], k, first_pos[s:e], max_pts, return_vertices, return_sq, timers,
+                                        None if boundaries is None else (boundaries[0][s:e], boundaries[1][s:e])))
         if len(parts) == 1:
             out = parts[0]
         else:
@@ -423,11 +428,15 @@ def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, ma
     ``totals_host()`` / ``metrics()`` / ``integers()`` is called on the result.
     ``timers``: optional dict filled with (start, end) CUDA-event pairs per kernel family."""
     yt, yp = _check_pair(y_true, y_pred)
-    lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries,
+    # the contour stage uses the label pass's boundary rows to skip the walk on layered maps
+    lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries or contours,
                     timers=timers)
     ct = None
     if contours:
-        ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts, timers=timers, check_overflow=False)
+        ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts, timers=timers, check_overflow=False,
+                          boundaries=(lp.bnd_true, lp.bnd_pred))
+        if not boundaries:
+            lp.bnd_true = lp.bnd_pred = None
     cls, bnd, tot = derive_on_device(lp, ct, yt.shape[0], timers)
     return SuiteResult(yt.shape[0], lp, ct, cls, bnd, tot, (yt, yp) if contours else None)
 
