@@ -907,10 +907,38 @@ struct ColumnParams {
     bool keep_d2;
 };
 
-__device__ __forceinline__ void coop_scan_range(const int4* src, int a, int b, int cy, int cx, int& bm) {
+// Query groups: kColGroup consecutive lanes share one column span (their sources are read from one address per
+// group: 32 / kColGroup distinct LDS.128 addresses per instruction, mostly in different banks).  Smaller groups
+// have narrower spans and a smaller flank radius (fewer vertex evaluations per query), at the price of shuffle
+// reductions inside the group.
+#ifndef OCTM_COL_GROUP
+#define OCTM_COL_GROUP 4
+#endif
+constexpr int kColGroup = OCTM_COL_GROUP;
+
+__device__ __forceinline__ int group_min(int v) {
+    if (kColGroup == 32) return __reduce_min_sync(0xffffffffu, v);
+#pragma unroll
+    for (int o = kColGroup / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int group_max(int v) {
+    if (kColGroup == 32) return __reduce_max_sync(0xffffffffu, v);
+#pragma unroll
+    for (int o = kColGroup / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// All lanes fold the sorted source vertices [a, a + len) of THEIR group into bm; the trip count is the warp's
+// maximum, so a group with a shorter range runs on into vertices it does not need (harmless: every entry is a
+// real vertex).  nsp = padded size of the sorted array; the start moves left when the 4-wide steps would
+// run past it.
+__device__ __forceinline__ void coop_scan_range(const int4* src, int a, int len, int nsp, int cy, int cx, int& bm) {
+    const int n = (__reduce_max_sync(0xffffffffu, len) + 3) & ~3;
+    const int4* p = src + min(a, nsp - n);
 #pragma unroll 1
-    for (int i = a; i < b; i += 4) {
-        const int4 s0 = src[i], s1 = src[i + 1], s2 = src[i + 2], s3 = src[i + 3];
+    for (int i = 0; i < n; i += 4) {
+        const int4 s0 = p[i], s1 = p[i + 1], s2 = p[i + 2], s3 = p[i + 3];
         const int m01 = min(s0.y * cx + (s0.x * cy + s0.z), s1.y * cx + (s1.x * cy + s1.z));
         const int m23 = min(s2.y * cx + (s2.x * cy + s2.z), s3.y * cx + (s3.x * cy + s3.z));
         bm = min(bm, min(m01, m23));
@@ -1033,19 +1061,21 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
                 int bm = 0x3fffffff;                   // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
                 for (;;) {
                     const bool mine = (part >> lane) & 1u;
-                    const int x0 = min(__reduce_min_sync(0xffffffffu, mine ? qx : 0x7fffffff), ncol - 1);
-                    const int x1 = min(__reduce_max_sync(0xffffffffu, mine ? qx : 0), ncol - 1);
-                    const int lo = static_cast<int>(col[x0]), hi = static_cast<int>(col[x1 + 1]);
-                    coop_scan_range(src, lo, hi, cy, cx, bm);
-                    const int bmax = __reduce_max_sync(0xffffffffu, mine ? bm + qn : 0);
+                    const int x0 = min(group_min(mine ? qx : 0x7fffffff), ncol - 1);
+                    const int x1 = min(group_max(mine ? qx : -1), ncol - 1);
+                    const bool has = x1 >= 0;          // this group has queries in this part
+                    const int lo = has ? static_cast<int>(col[x0]) : 0, hi = has ? static_cast<int>(col[x1 + 1]) : 0;
+                    coop_scan_range(src, lo, hi - lo, ns + 3, cy, cx, bm);
+                    const int bmax = group_max(mine ? bm + qn : 0);
                     // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
                     // (the approximate square root is exact enough below 2^20; real distances are below 2^29)
                     float rf;
                     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(static_cast<float>(bmax)));
                     const int r = bmax >= 0x3fffffff ? ncol : static_cast<int>(rf) + (bmax >= (1 << 20) ? 1 : 0);
-                    const int fl = static_cast<int>(col[max(x0 - r, 0)]), fr = static_cast<int>(col[min(x1 + r, ncol - 1) + 1]);
-                    coop_scan_range(src, fl, lo, cy, cx, bm);
-                    coop_scan_range(src, hi, fr, cy, cx, bm);
+                    const int fl = has ? static_cast<int>(col[max(x0 - r, 0)]) : 0;
+                    const int fr = has ? static_cast<int>(col[min(x1 + r, ncol - 1) + 1]) : 0;
+                    coop_scan_range(src, fl, lo - fl, ns + 3, cy, cx, bm);
+                    coop_scan_range(src, hi, fr - hi, ns + 3, cy, cx, bm);
                     if (part == 0xffffffffu || (part & 1u) == 0) break;
                     part = ~part;                      // the queries after the seam
                 }
