@@ -259,7 +259,12 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
             if (lane == 31) hr = hfirst_next;
             if (x + 1 >= W) hr = h;
             hleft = __shfl_sync(0xffffffffu, h, 31);
-            if (!__all_sync(0xffffffffu, !valid || static_cast<unsigned>(h - 1) <= static_cast<unsigned>(H - 2))) { ok = false; break; }
+            // all three heights inside [1, H - 1] before any pixel is addressed through them (the right neighbour of
+            // lane 31 belongs to the next block and has not been looked at yet)
+            const bool inside = static_cast<unsigned>(h - 1) <= static_cast<unsigned>(H - 2) &&
+                                static_cast<unsigned>(hl - 1) <= static_cast<unsigned>(H - 2) &&
+                                static_cast<unsigned>(hr - 1) <= static_cast<unsigned>(H - 2);
+            if (!__all_sync(0xffffffffu, !valid || inside)) { ok = false; break; }
             const int lo = min(hl, min(h, hr)) - 1, hi = max(hl, max(h, hr));
             // rows as 32-bit offsets from the column's first pixel (H * W < 2^31 on this path)
             const uint8_t* colp = L + xc;

@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
     python bench.py $SMALL > gpurun_out/ncu_launches_$TAG.log 2>&1
 python bench.py $SMALL > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k regex:'label_pass_fast|trace_kernel|distance_column_kernel|distance_search_kernel|distance_select_kernel|derive_kernel' -s 5 -c 5 \
+    -k regex:'label_pass_fast|trace_layered_kernel|trace_kernel|distance_column_kernel|distance_search_kernel|distance_select_kernel|derive_kernel' -s 6 -c 6 \
     -o gpurun_out/prof_$TAG python bench.py $SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
