@@ -32,7 +32,7 @@ H, W, K = 496, 512, 8
 BYTES_PER_BSCAN = 2 * H * W                      # algorithmic (compulsory) label bytes, SURVEY.md 8(d)
 WORKLOAD = "cfg4: full metric suite, synthetic layered 496x512 B-scans, 8 classes"
 # DRAM traffic of label_pass_fast per B-scan from the ncu --set full capture of this workload
-# (profiles/r1_v8_ncu_summary.md: dram__bytes_read 1.041625 GB + dram__bytes_write 4.222 MB for 2048 B-scans)
+# (profiles/r1_v8_ncu_summary.md: dram__bytes_read 1.041608 GB + dram__bytes_write 11.885 MB for 2048 B-scans)
 NCU_TRAFFIC_BYTES_PER_BSCAN = (1.041608e9 + 11.885312e6) / 2048
 
 
