@@ -917,7 +917,7 @@ struct ColumnParams {
 // have narrower spans and a smaller flank radius (fewer vertex evaluations per query), at the price of shuffle
 // reductions inside the group.
 #ifndef OCTM_COL_GROUP
-#define OCTM_COL_GROUP 4
+#define OCTM_COL_GROUP 2
 #endif
 constexpr int kColGroup = OCTM_COL_GROUP;
 
@@ -934,19 +934,30 @@ __device__ __forceinline__ int group_max(int v) {
     return v;
 }
 
-// All lanes fold the sorted source vertices [a, a + len) of THEIR group into bm; the trip count is the warp's
+// Queries per lane: a lane holds kColQ consecutive query vertices, so one broadcast LDS.128 of a source vertex
+// feeds kColQ evaluations and the per-chunk bookkeeping (spans, look-ups, loops) is shared by 32 * kColQ queries.
+#ifndef OCTM_COL_Q
+#define OCTM_COL_Q 2
+#endif
+constexpr int kColQ = OCTM_COL_Q;
+
+// All lanes fold the sorted source vertices [a, a + len) of THEIR group into bm[]; the trip count is the warp's
 // maximum, so a group with a shorter range runs on into vertices it does not need (harmless: every entry is a
 // real vertex).  nsp = padded size of the sorted array; the start moves left when the 4-wide steps would
 // run past it.
-__device__ __forceinline__ void coop_scan_range(const int4* src, int a, int len, int nsp, int cy, int cx, int& bm) {
+__device__ __forceinline__ void coop_scan_range(const int4* src, int a, int len, int nsp, const int (&cy)[kColQ],
+                                                const int (&cx)[kColQ], int (&bm)[kColQ]) {
     const int n = (__reduce_max_sync(0xffffffffu, len) + 3) & ~3;
     const int4* p = src + min(a, nsp - n);
 #pragma unroll 1
     for (int i = 0; i < n; i += 4) {
         const int4 s0 = p[i], s1 = p[i + 1], s2 = p[i + 2], s3 = p[i + 3];
-        const int m01 = min(s0.y * cx + (s0.x * cy + s0.z), s1.y * cx + (s1.x * cy + s1.z));
-        const int m23 = min(s2.y * cx + (s2.x * cy + s2.z), s3.y * cx + (s3.x * cy + s3.z));
-        bm = min(bm, min(m01, m23));
+#pragma unroll
+        for (int q = 0; q < kColQ; ++q) {
+            const int m01 = min(s0.y * cx[q] + (s0.x * cy[q] + s0.z), s1.y * cx[q] + (s1.x * cy[q] + s1.z));
+            const int m23 = min(s2.y * cx[q] + (s2.x * cy[q] + s2.z), s3.y * cx[q] + (s3.x * cy[q] + s3.z));
+            bm[q] = min(bm[q], min(m01, m23));
+        }
     }
 }
 
@@ -981,7 +992,7 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
         const uint32_t* vs = prm.verts + (pair * 2 + dir) * static_cast<long long>(cap);
         const uint32_t* vq = prm.verts + (pair * 2 + 1 - dir) * static_cast<long long>(cap);
         uint32_t* dq = prm.d2 + unit * static_cast<long long>(cap);
-        const int nchunks = (nq + 31) >> 5;
+        const int nchunks = (nq + 32 * kColQ - 1) / (32 * kColQ);
         {   // pull the next unit's vertex lists towards L2 while this one is searched
             const long long nu = unit + gridDim.x;
             if (nu < prm.n_units) {
@@ -1053,25 +1064,50 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
         for (;;) {
 #pragma unroll 1
             for (int c = warp; c < nchunks; c += kWarps) {
-                const int j = c * 32 + lane;
-                const uint32_t v = vq[min(j, nq - 1)];          // tail lanes repeat the last query
-                const int qy = v >> 16, qx = v & 0xffff;
-                const int cy = -2 * qy, cx = -2 * qx, qn = qy * qy + qx * qx;
+                // lane l holds the consecutive queries c * 32 Q + l Q .. + Q - 1 (tail lanes repeat the last query)
+                const int j0 = (c * 32 + lane) * kColQ;
+                int qx[kColQ], cy[kColQ], cx[kColQ], qn[kColQ], bm[kColQ];
+#pragma unroll
+                for (int q = 0; q < kColQ; ++q) {
+                    const uint32_t v = vq[min(j0 + q, nq - 1)];
+                    const int qy = v >> 16;
+                    qx[q] = v & 0xffff;
+                    cy[q] = -2 * qy; cx[q] = -2 * qx[q]; qn[q] = qy * qy + qx[q] * qx[q];
+                    bm[q] = 0x3fffffff;                // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
+                }
                 // Consecutive polyline vertices are at most 2 columns apart; a larger step is the seam between the
-                // forward and the backward run of an open contour (or the closing repeat): the queries before and
-                // after it get their own column span, so that no span covers the columns in between.
-                const int qprev = __shfl_up_sync(0xffffffffu, qx, 1);
-                const uint32_t seam = __ballot_sync(0xffffffffu, lane > 0 && abs(qx - qprev) > 2);
-                uint32_t part = seam ? (1u << (__ffs(seam) - 1)) - 1u : 0xffffffffu;
-                int bm = 0x3fffffff;                   // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
-                for (;;) {
-                    const bool mine = (part >> lane) & 1u;
-                    const int x0 = min(group_min(mine ? qx : 0x7fffffff), ncol - 1);
-                    const int x1 = min(group_max(mine ? qx : -1), ncol - 1);
+                // forward and the backward run of a walked open contour (or the closing repeat): the queries before
+                // and after it get their own column span, so that no span covers the columns in between.
+                // first = index (in this chunk's 32 Q queries) of the first query after the seam.
+                int first = 32 * kColQ;
+                {
+                    const int qprev = __shfl_up_sync(0xffffffffu, qx[kColQ - 1], 1);
+#pragma unroll
+                    for (int q = 0; q < kColQ; ++q) {
+                        const bool jump = q == 0 ? (lane > 0 && abs(qx[0] - qprev) > 2) : abs(qx[q] - qx[q - 1]) > 2;
+                        const uint32_t m = __ballot_sync(0xffffffffu, jump);
+                        if (m) first = min(first, (__ffs(m) - 1) * kColQ + q);
+                    }
+                }
+                for (int part = 0;; ++part) {          // part 0: queries before `first`, part 1: the rest
+                    int x0 = 0x7fffffff, x1 = -1, bmine = 0;
+#pragma unroll
+                    for (int q = 0; q < kColQ; ++q) {
+                        const bool mine = ((lane * kColQ + q) < first) == (part == 0);
+                        x0 = min(x0, mine ? qx[q] : 0x7fffffff);
+                        x1 = max(x1, mine ? qx[q] : -1);
+                    }
+                    x0 = min(group_min(x0), ncol - 1);
+                    x1 = min(group_max(x1), ncol - 1);
                     const bool has = x1 >= 0;          // this group has queries in this part
                     const int lo = has ? static_cast<int>(col[x0]) : 0, hi = has ? static_cast<int>(col[x1 + 1]) : 0;
                     coop_scan_range(src, lo, hi - lo, ns + 3, cy, cx, bm);
-                    const int bmax = group_max(mine ? bm + qn : 0);
+#pragma unroll
+                    for (int q = 0; q < kColQ; ++q) {
+                        const bool mine = ((lane * kColQ + q) < first) == (part == 0);
+                        bmine = max(bmine, mine ? bm[q] + qn[q] : 0);
+                    }
+                    const int bmax = group_max(bmine);
                     // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
                     // (the approximate square root is exact enough below 2^20; real distances are below 2^29)
                     float rf;
@@ -1081,12 +1117,16 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
                     const int fr = has ? static_cast<int>(col[min(x1 + r, ncol - 1) + 1]) : 0;
                     coop_scan_range(src, fl, lo - fl, ns + 3, cy, cx, bm);
                     coop_scan_range(src, hi, fr - hi, ns + 3, cy, cx, bm);
-                    if (part == 0xffffffffu || (part & 1u) == 0) break;
-                    part = ~part;                      // the queries after the seam
+                    if (part == 1 || first == 32 * kColQ) break;
                 }
-                const int bestd = bm + qn;
-                if ((!count || prm.keep_d2) && j < nq) dq[j] = static_cast<uint32_t>(bestd);
-                if (count) count_minima(bestd, j < nq, lane, s_bins, run_max, run_bad);
+                const bool store = !count || prm.keep_d2;
+#pragma unroll
+                for (int q = 0; q < kColQ; ++q) {
+                    const int bestd = bm[q] + qn[q];
+                    const bool valid = j0 + q < nq;
+                    if (store && valid) dq[j0 + q] = static_cast<uint32_t>(bestd);
+                    if (count) count_minima(bestd, valid, lane, s_bins, run_max, run_bad);
+                }
             }
             if (!count) break;
             publish_counts(run_max, run_bad, lane, &s_vmax, &s_big);
