@@ -1004,8 +1004,33 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
             }
         }
         if (!synced) __syncthreads();                  // every warp is done with the previous unit's tables
-        for (int i = threadIdx.x; i <= ncol; i += kColThreads) col[i] = 0;
         if (threadIdx.x == 0) { s_vmax = 0; s_big = 0; }
+        // A contour that is already in column order (what trace_layered_kernel emits) needs no sort: one pass copies
+        // the vertices and fills col[] from the places where the column changes -- col[c] = number of vertices left
+        // of column c.  Done optimistically; the vote below tells whether the order held.
+        bool sorted = true;
+        {
+            const int xfirst = min(static_cast<int>(vs[0] & 0xffffu), ncol - 1);
+            const int xlast = min(static_cast<int>(vs[ns - 1] & 0xffffu), ncol - 1);
+            for (int i = threadIdx.x; i < ns; i += kColThreads) {
+                const uint32_t v = vs[i];
+                const int y = v >> 16, xr = v & 0xffff, x = min(xr, ncol - 1);
+                const int xp = i > 0 ? min(static_cast<int>(vs[i - 1] & 0xffffu), ncol - 1) : x;
+                sorted &= x >= xp;
+                src[i] = make_int4(y, xr, y * y + xr * xr, 0);
+                if (i < 3) src[ns + i] = make_int4(y, xr, y * y + xr * xr, 0);   // padding for the 4-wide scans
+                for (int c = xp + 1; c <= x; ++c) col[c] = static_cast<uint32_t>(i);
+            }
+            if (threadIdx.x < 3 && threadIdx.x >= ns) {                      // fewer than three vertices
+                const uint32_t v = vs[0];
+                const int y = v >> 16, x = v & 0xffff;
+                src[ns + threadIdx.x] = make_int4(y, x, y * y + x * x, 0);
+            }
+            for (int c = threadIdx.x; c <= xfirst; c += kColThreads) col[c] = 0;
+            for (int c = xlast + 1 + threadIdx.x; c <= ncol; c += kColThreads) col[c] = static_cast<uint32_t>(ns);
+        }
+        if (!__syncthreads_and(sorted)) {
+        for (int i = threadIdx.x; i <= ncol; i += kColThreads) col[i] = 0;
         __syncthreads();
         // counting sort by column: count into col[x + 1] ...
         for (int i = threadIdx.x; i < ns; i += kColThreads) {
@@ -1055,6 +1080,7 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
             src[ns + threadIdx.x] = make_int4(y, x, y * y + x * x, 0);
         }
         __syncthreads();
+        }
 
         // The final minima are counted (16-bit counters, one per even value) instead of stored; a unit with a value
         // the counters cannot hold repeats the search in store mode and is left to distance_select_kernel.
