@@ -200,11 +200,11 @@ __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const Trace
 // On a layered B-scan contour [0] of a class mask is the boundary between "mask as at pixel (0, 0)" above and
 // the rest below, running from the left to the right image border: a height function h(x).  The label pass
 // already knows a candidate: h(x) = #{label < k} in column x (its boundary rows).  This kernel checks the
-// candidate instead of walking it: one WARP per (item, class, map), 32 adjacent columns at a time, a lane each:
+// candidate instead of walking it: one WARP per (item, class, map), 64 adjacent columns at a time, two per lane:
 //   * 1 <= h(x) <= H - 1 everywhere;
 //   * every pixel of every 2x2 square the walk would visit has the value the step function predicts: in column
 //     x the rows [min(h(x-1), h(x), h(x+1)) - 1, max(..)] hold "mask(0,0)" above h(x) and the opposite from h(x)
-//     down (byte loads, adjacent lanes = adjacent columns, four rows in flight);
+//     down (16-bit loads, adjacent lanes = adjacent column pairs, four rows in flight);
 //   * the raster-first pixel of the path is the seed the label pass found (no pixel of the class above it).
 // The walk is a deterministic function of exactly these pixels and starts at the seed's square, so when all
 // three hold it would trace this very polyline.  Its vertices -- (2 h(x) - 1, 2 x) per column and (2 r, 2 x + 1)
@@ -244,61 +244,73 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
         const int* hrow = (m ? prm.bnd_p : prm.bnd_t) + (item * (K - 1) + (ok ? brow : 0)) * static_cast<long long>(W);
         uint32_t base = 0, minkey = 0xffffffffu;
         bool bad = false;
+        // 64 columns per step, two adjacent columns (2 l, 2 l + 1) per lane: W is even on this path
+        const int2* hrow2 = reinterpret_cast<const int2*>(hrow);
+        const int W2 = W >> 1;
         int hleft = 0;                                     // h of the column left of this block
-        int hcur = ok ? hrow[min(lane, W - 1)] : 1;
-        for (int x0 = 0; ok && x0 < W; x0 += 32) {
-            const int x = x0 + lane;
+        int2 hcur = ok ? hrow2[min(lane, W2 - 1)] : make_int2(1, 1);
+        for (int x0 = 0; ok && x0 < W; x0 += 64) {
+            const int x = x0 + 2 * lane;                   // this lane's first column
             const bool valid = x < W;
-            const int xc = min(x, W - 1);
-            const int h = hcur;
-            hcur = hrow[min(x + 32, W - 1)];               // next block's heights, in flight during this block's checks
-            int hl = __shfl_up_sync(0xffffffffu, h, 1);
-            if (lane == 0) hl = x0 > 0 ? hleft : h;
-            int hr = __shfl_down_sync(0xffffffffu, h, 1);
-            const int hfirst_next = __shfl_sync(0xffffffffu, hcur, 0);
+            const int xc = min(x, W - 2);
+            const int ha = hcur.x, hb = hcur.y;
+            hcur = hrow2[min((x0 >> 1) + 32 + lane, W2 - 1)];      // next block's heights, in flight during the checks
+            int hl = __shfl_up_sync(0xffffffffu, hb, 1);
+            if (lane == 0) hl = x0 > 0 ? hleft : ha;
+            int hr = __shfl_down_sync(0xffffffffu, ha, 1);
+            const int hfirst_next = __shfl_sync(0xffffffffu, hcur.x, 0);
             if (lane == 31) hr = hfirst_next;
-            if (x + 1 >= W) hr = h;
-            hleft = __shfl_sync(0xffffffffu, h, 31);
-            // all three heights inside [1, H - 1] before any pixel is addressed through them (the right neighbour of
+            if (x + 2 >= W) hr = hb;
+            hleft = __shfl_sync(0xffffffffu, hb, 31);
+            // all heights inside [1, H - 1] before any pixel is addressed through them (the right neighbour of
             // lane 31 belongs to the next block and has not been looked at yet)
-            const bool inside = static_cast<unsigned>(h - 1) <= static_cast<unsigned>(H - 2) &&
-                                static_cast<unsigned>(hl - 1) <= static_cast<unsigned>(H - 2) &&
-                                static_cast<unsigned>(hr - 1) <= static_cast<unsigned>(H - 2);
+            const unsigned hm = static_cast<unsigned>(H - 2);
+            const bool inside = static_cast<unsigned>(ha - 1) <= hm && static_cast<unsigned>(hb - 1) <= hm &&
+                                static_cast<unsigned>(hl - 1) <= hm && static_cast<unsigned>(hr - 1) <= hm;
             if (!__all_sync(0xffffffffu, !valid || inside)) { ok = false; break; }
-            const int lo = min(hl, min(h, hr)) - 1, hi = max(hl, max(h, hr));
-            // rows as 32-bit offsets from the column's first pixel (H * W < 2^31 on this path)
+            // windows of the two columns as 32-bit pixel offsets (H * W < 2^31 on this path)
+            const int loa = (min(hl, min(ha, hb)) - 1) * W, hia = max(hl, max(ha, hb)) * W;
+            const int lob = (min(ha, min(hb, hr)) - 1) * W, hib = max(ha, max(hb, hr)) * W;
+            const int olo = min(loa, lob), ohi = max(hia, hib), oha = ha * W, ohb = hb * W;
             const uint8_t* colp = L + xc;
-            const int olo = lo * W, ohi = hi * W, oh = h * W;
-            const int nrows = __reduce_max_sync(0xffffffffu, valid ? hi - lo + 1 : 0);
-            for (int u0 = 0; u0 < nrows; u0 += 4) {        // four rows in flight
+            const int nrows = __reduce_max_sync(0xffffffffu, valid ? (ohi - olo) / W + 1 : 0);
+            for (int u0 = 0; u0 < nrows; u0 += 4) {        // four rows in flight, two pixels each
                 int off[4];
                 uint32_t px[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {              // past the window: its last row again (harmless)
                     off[u] = min(olo + (u0 + u) * W, ohi);
-                    px[u] = __ldg(colp + off[u]);
+                    px[u] = __ldg(reinterpret_cast<const unsigned short*>(colp + off[u]));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) bad |= ((px[u] == static_cast<uint32_t>(cls)) != (off[u] >= oh)) != inv;
+                for (int u = 0; u < 4; ++u) {
+                    const bool ea = (px[u] & 0xffu) == static_cast<uint32_t>(cls), eb = (px[u] >> 8) == static_cast<uint32_t>(cls);
+                    bad |= off[u] >= loa && off[u] <= hia && ((ea != (off[u] >= oha)) != inv);
+                    bad |= off[u] >= lob && off[u] <= hib && ((eb != (off[u] >= ohb)) != inv);
+                }
             }
             // vertices of these columns at their left-to-right positions
-            const int dh = abs(hr - h);
-            const uint32_t cnt = valid ? 1u + static_cast<uint32_t>(dh) : 0u;
+            const int da = abs(hb - ha), db = abs(hr - hb);
+            const uint32_t cnt = valid ? 2u + static_cast<uint32_t>(da + db) : 0u;
             uint32_t incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += up;
             }
-            const uint32_t pos = base + incl - cnt;
+            uint32_t pos = base + incl - cnt;
             base += __shfl_sync(0xffffffffu, incl, 31);
             if (base > cap) { ok = false; break; }         // too long: the walk flags the overflow
             if (valid) {
                 const uint32_t x2 = 2u * static_cast<uint32_t>(x);
-                minkey = min(minkey, static_cast<uint32_t>(h) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x));
-                out[pos] = (static_cast<uint32_t>(2 * h - 1) << 16) | x2;
-                const int ra = min(h, hr);
-                for (int t = 0; t < dh; ++t) out[pos + 1 + t] = (static_cast<uint32_t>(2 * (ra + t)) << 16) | (x2 + 1u);
+                const uint32_t ua = static_cast<uint32_t>(ha), ub = static_cast<uint32_t>(hb), uw = static_cast<uint32_t>(W);
+                minkey = min(minkey, min(ua * uw + static_cast<uint32_t>(x), ub * uw + static_cast<uint32_t>(x) + 1u));
+                out[pos++] = (static_cast<uint32_t>(2 * ha - 1) << 16) | x2;
+                const int ra = min(ha, hb);
+                for (int t = 0; t < da; ++t) out[pos++] = (static_cast<uint32_t>(2 * (ra + t)) << 16) | (x2 + 1u);
+                out[pos++] = (static_cast<uint32_t>(2 * hb - 1) << 16) | (x2 + 2u);
+                const int rb = min(hb, hr);
+                for (int t = 0; t < db; ++t) out[pos++] = (static_cast<uint32_t>(2 * (rb + t)) << 16) | (x2 + 3u);
             }
         }
         if (ok) ok = !__any_sync(0xffffffffu, bad) && __reduce_min_sync(0xffffffffu, minkey) == seed;
@@ -1338,7 +1350,9 @@ extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_p
     const long long threads = n_items * num_classes * 2;
     // layered fast path (needs the label pass's boundary rows): OCTM_TRACE_LAYERED=0 turns it off
     static const bool env_layered = [] { const char* e = getenv("OCTM_TRACE_LAYERED"); return !(e && e[0] == '0'); }();
-    if (env_layered && bnd_true != nullptr && H >= 2 && num_classes >= 2 && num_classes <= 32) {
+    if (env_layered && bnd_true != nullptr && H >= 2 && W % 2 == 0 && num_classes >= 2 && num_classes <= 32 &&
+        reinterpret_cast<uintptr_t>(y_true) % 2 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 2 == 0 &&
+        reinterpret_cast<uintptr_t>(bnd_true) % 8 == 0 && reinterpret_cast<uintptr_t>(bnd_pred) % 8 == 0) {
         int fit = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_layered_kernel, 128, 0) != cudaSuccess || fit < 1) {
             cudaGetLastError();
