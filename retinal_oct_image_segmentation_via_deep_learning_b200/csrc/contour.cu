@@ -1100,6 +1100,8 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
         uint32_t run_max = 0;
         bool run_bad = false;
         for (;;) {
+            // chunks are dealt out statically: a shared counter balances the warps slightly better but costs more
+            // than it saves (measured 3.96 vs 3.84 ms)
 #pragma unroll 1
             for (int c = warp; c < nchunks; c += kWarps) {
                 // lane l holds the consecutive queries c * 32 Q + l Q .. + Q - 1 (tail lanes repeat the last query)
