@@ -44,7 +44,8 @@ def test_layered_maps_take_the_fast_path(cuda):
 @pytest.mark.parametrize("h,w,k,kw", [(200, 256, 6, dict(noise=0.002)), (64, 512, 4, dict(jitter=3.0)),
                                       (96, 48, 3, dict()), (130, 512, 8, dict(min_gap=1, jitter=2.5)),
                                       (40, 32, 2, dict()), (37, 50, 3, dict()), (45, 33, 3, dict()),
-                                      (64, 130, 5, dict(jitter=2.0))])
+                                      (64, 130, 5, dict(jitter=2.0)), (120, 96, 10, dict()), (200, 64, 16, dict(noise=0.001)),
+                                      (2, 64, 2, dict()), (3, 32, 2, dict())])
 def test_layered_variants_and_noise(cuda, h, w, k, kw):
     yt, yp = synth.layered_pair(5, h, w, k, seed=77 + h, **kw)
     _assert_same(*_both(yt, yp, k, cuda))
