@@ -47,6 +47,7 @@ extern "C" {
 #define OCTM_DTYPE_F16 1
 #define OCTM_DTYPE_BF16 2
 #define OCTM_DTYPE_F64 3
+#define OCTM_DTYPE_I32 4
 
 #define OCTM_MAX_CLASSES 16
 #define OCTM_NO_SEED 0xFFFFFFFFu
@@ -176,6 +177,17 @@ OCTM_API int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pt
                             int num_classes, int max_pts, int H, int W /* shape the vertices were traced on */,
                             uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, uint32_t* d2, int keep_d2,
                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Boundary rows -> label maps (the layer datasets catalogued in the reference's
+ * Datasets.md:3-26 annotate boundary curves, while Metrics/*.py score masks).  The inverse of the label
+ * pass's boundary rows on layered maps:
+ *   labels[i][y][x] = #{ k : b_k(i, x) <= y }
+ *   boundaries  [n][num_boundaries][W] of dtype OCTM_DTYPE_I32 or OCTM_DTYPE_F32, any order per column, any
+ *               value (outside [0, H]: the layer is empty / fills the column); NaN = boundary absent
+ *   labels      uint8 [n][H][W], values 0 .. num_boundaries (<= 15) */
+OCTM_API int octm_labels_from_boundaries(const void* boundaries, int dtype, int64_t n_items, int num_boundaries,
+                                int H, int W, uint8_t* labels, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 3-D surface-distance metrics (BASELINE config 5; the reference's contour metrics are 2-D only, this is

@@ -118,3 +118,17 @@ def score_bscan_fast(y_true, y_pred, num_classes):
         "boundary_true": bt, "boundary_pred": bp,
         "boundary_sq": (d * d).sum(axis=1), "boundary_abs": np.abs(d).sum(axis=1),
     }
+
+
+def labels_from_boundaries(boundaries, height):
+    """label[i, y, x] = #{k : b_k(i, x) <= y}; NaN boundaries are counted for no row (build-defined, the inverse of
+    boundary extraction on layered maps; include/octm.h octm_labels_from_boundaries)."""
+    b = np.asarray(boundaries)
+    n, kb, w = b.shape
+    y = np.arange(int(height), dtype=np.float64)[None, :, None]
+    lab = np.zeros((n, int(height), w), dtype=np.uint8)
+    for k in range(kb):
+        bk = b[:, k, None, :].astype(np.float64)
+        with np.errstate(invalid="ignore"):
+            lab += (bk <= y).astype(np.uint8)
+    return lab

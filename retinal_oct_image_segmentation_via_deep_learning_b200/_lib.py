@@ -20,7 +20,7 @@ CLASS_METRICS = ("accuracy", "sensitivity", "cm_precision", "specificity", "dice
                  "region_precision", "recall", "mean_squared_error", "root_mean_squared_error", "mad",
                  "vascularity_index", "thickness_difference", "hausdorff_distance", "hausdorff_distance_95", "assd")
 BOUNDARY_METRICS = ("boundary_mse", "boundary_rmse", "boundary_mad")
-DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
+DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64, DTYPE_I32 = 0, 1, 2, 3, 4
 
 _c = ctypes
 _P = _c.c_void_p
@@ -52,6 +52,7 @@ SIGNATURES = {
     "octm_surface3d_u8": (_INT, [_P, _P, _INT, _INT, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
     "octm_host_pack_nibbles": (_INT, [_P, _P, _c.c_size_t, _INT]),
     "octm_unpack_nibbles_u8": (_INT, [_P, _I64, _P, _P]),
+    "octm_labels_from_boundaries": (_INT, [_P, _INT, _I64, _INT, _INT, _INT, _P, _P]),
     "octm_totals_len": (_INT, [_INT]),
     "octm_derive_metrics": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P]),
 }

@@ -1,0 +1,163 @@
+"""Host-side readers for the on-disk formats of the OCT datasets the reference catalogues
+(reference ``Datasets.md:3-26``).  The reference ships no loader code, so these follow
+the published file formats, not reference lines:
+
+* MetaImage ``.mhd`` + ``.raw`` / ``.zraw`` (RETOUCH volumes and reference masks): ``read_mhd`` / ``write_mhd``;
+* MATLAB ``.mat`` with boundary annotations (Duke DME / AMD: ``manualLayers1`` of shape boundaries x columns x
+  B-scans, NaN where a column is not annotated): ``read_mat_layers``;
+* ``.npy`` / ``.npz`` label volumes: ``read_labels``.
+
+Everything here is plain host I/O (numpy, scipy.io for ``.mat``); the arrays go to the GPU through
+``suite.evaluate_host`` (label volumes) or ``suite.labels_from_boundaries`` (boundary curves -> label maps).
+"""
+from __future__ import annotations
+
+import os
+import zlib
+
+import numpy as np
+
+_MHD_TYPES = {"MET_UCHAR": np.uint8, "MET_CHAR": np.int8, "MET_USHORT": np.uint16, "MET_SHORT": np.int16,
+              "MET_UINT": np.uint32, "MET_INT": np.int32, "MET_FLOAT": np.float32, "MET_DOUBLE": np.float64}
+_MHD_NAMES = {np.dtype(v): k for k, v in _MHD_TYPES.items()}
+
+
+def read_mhd(path):
+    """MetaImage header + raw data -> (array in C order ``[..., dim1, dim0]`` = ``[slices, rows, cols]`` for a
+    volume, header dict).  Supports ``ElementDataFile = <file> | LOCAL``, ``CompressedData`` (zlib),
+    ``BinaryDataByteOrderMSB`` and ``HeaderSize``."""
+    with open(path, "rb") as f:
+        blob = f.read()
+    header, pos = {}, 0
+    while True:
+        end = blob.find(b"\n", pos)
+        if end < 0:
+            raise ValueError(f"{path}: no ElementDataFile line")
+        line = blob[pos:end].decode("latin-1").strip()
+        pos = end + 1
+        if not line:
+            continue
+        if "=" not in line:
+            raise ValueError(f"{path}: malformed header line {line!r}")
+        key, val = (s.strip() for s in line.split("=", 1))
+        header[key] = val
+        if key == "ElementDataFile":
+            break
+    if header.get("ObjectType", "Image") != "Image":
+        raise ValueError(f"{path}: ObjectType {header['ObjectType']!r} is not an image")
+    ndims = int(header["NDims"])
+    dims = [int(v) for v in header["DimSize"].split()]
+    if len(dims) != ndims:
+        raise ValueError(f"{path}: DimSize has {len(dims)} entries, NDims = {ndims}")
+    if header["ElementType"] not in _MHD_TYPES:
+        raise ValueError(f"{path}: unsupported ElementType {header['ElementType']}")
+    channels = int(header.get("ElementNumberOfChannels", "1"))
+    dtype = np.dtype(_MHD_TYPES[header["ElementType"]])
+    if header.get("BinaryDataByteOrderMSB", header.get("ElementByteOrderMSB", "False")).lower() == "true":
+        dtype = dtype.newbyteorder(">")
+    data_file = header["ElementDataFile"]
+    if data_file == "LOCAL":
+        raw = blob[pos:]
+    else:
+        if "%" in data_file or data_file == "LIST":
+            raise ValueError(f"{path}: one-file-per-slice data ({data_file}) is not supported")
+        with open(os.path.join(os.path.dirname(os.path.abspath(path)), data_file), "rb") as f:
+            raw = f.read()
+    skip = int(header.get("HeaderSize", "0"))
+    if skip > 0:
+        raw = raw[skip:]
+    if header.get("CompressedData", "False").lower() == "true":
+        raw = zlib.decompress(raw)
+    count = int(np.prod(dims)) * channels
+    if len(raw) < count * dtype.itemsize:
+        raise ValueError(f"{path}: data file holds {len(raw)} bytes, header needs {count * dtype.itemsize}")
+    arr = np.frombuffer(raw, dtype=dtype, count=count)
+    shape = tuple(reversed(dims)) + ((channels,) if channels > 1 else ())
+    return arr.reshape(shape).astype(dtype.newbyteorder("="), copy=False), header
+
+
+def write_mhd(path, array, spacing=None, compressed=False):
+    """Write ``array`` (C order ``[slices, rows, cols]``) as ``path`` (.mhd) + a sibling .raw / .zraw file."""
+    array = np.ascontiguousarray(array)
+    if array.dtype not in _MHD_NAMES:
+        raise TypeError(f"unsupported dtype {array.dtype}")
+    base = os.path.splitext(os.path.basename(path))[0] + (".zraw" if compressed else ".raw")
+    payload = array.tobytes()
+    if compressed:
+        payload = zlib.compress(payload)
+    lines = ["ObjectType = Image", f"NDims = {array.ndim}", "BinaryData = True", "BinaryDataByteOrderMSB = False",
+             f"CompressedData = {'True' if compressed else 'False'}"]
+    if compressed:
+        lines.append(f"CompressedDataSize = {len(payload)}")
+    if spacing is not None:
+        lines.append("ElementSpacing = " + " ".join(str(float(s)) for s in spacing))
+    lines += ["DimSize = " + " ".join(str(d) for d in reversed(array.shape)),
+              f"ElementType = {_MHD_NAMES[array.dtype]}", f"ElementDataFile = {base}"]
+    with open(path, "w", encoding="latin-1", newline="\n") as f:
+        f.write("\n".join(lines) + "\n")
+    with open(os.path.join(os.path.dirname(os.path.abspath(path)), base), "wb") as f:
+        f.write(payload)
+
+
+def read_mat_layers(path, key=None):
+    """Boundary annotations of a Duke-style ``.mat`` file -> float32 ``[B-scans, boundaries, columns]`` with NaN
+    where a column is not annotated (ready for ``suite.labels_from_boundaries``), plus the image stack
+    ``[B-scans, rows, columns]`` when the file has one (``images``), else None.  ``key`` defaults to the first
+    of ``manualLayers1``, ``manualLayers2``, ``automaticLayersDME``, ``automaticLayersNormal``, ``layerMaps``."""
+    from scipy.io import loadmat            # scipy is a dependency of the reference's own stack
+    mat = loadmat(path)
+    names = [key] if key else ["manualLayers1", "manualLayers2", "automaticLayersDME", "automaticLayersNormal", "layerMaps"]
+    found = next((n for n in names if n in mat), None)
+    if found is None:
+        raise KeyError(f"{path}: none of {names} present (variables: {sorted(k for k in mat if not k.startswith('__'))})")
+    layers = np.asarray(mat[found], dtype=np.float32)
+    if layers.ndim != 3:
+        raise ValueError(f"{path}: {found} has shape {layers.shape}, expected 3 dimensions")
+    if found == "layerMaps":                 # AMD set: B-scans x columns x boundaries
+        layers = np.transpose(layers, (0, 2, 1))
+    else:                                    # DME set: boundaries x columns x B-scans
+        layers = np.transpose(layers, (2, 0, 1))
+    images = None
+    if "images" in mat and np.asarray(mat["images"]).ndim == 3:
+        images = np.transpose(np.asarray(mat["images"]), (2, 0, 1))     # rows x columns x B-scans on disk
+    return np.ascontiguousarray(layers), images
+
+
+def annotated_scans(layers, min_fraction=0.5):
+    """Indices of the B-scans whose boundary rows are annotated in at least ``min_fraction`` of the columns
+    (the Duke DME volumes annotate 11 of 61 B-scans)."""
+    frac = np.isfinite(layers).all(axis=1).mean(axis=1)
+    return np.nonzero(frac >= min_fraction)[0]
+
+
+def read_labels(path, key=None):
+    """uint8 label volume ``[slices, rows, cols]`` from ``.npy`` / ``.npz`` / ``.mhd``."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npy":
+        arr = np.load(path)
+    elif ext == ".npz":
+        with np.load(path) as z:
+            arr = z[key if key else z.files[0]]
+    elif ext == ".mhd":
+        arr, _ = read_mhd(path)
+    else:
+        raise ValueError(f"unsupported label file {path}")
+    if arr.ndim == 2:
+        arr = arr[None]
+    if arr.ndim != 3:
+        raise ValueError(f"{path}: expected a 2-D or 3-D label array, got shape {arr.shape}")
+    if arr.dtype != np.uint8:
+        if arr.min() < 0 or arr.max() > 255:
+            raise ValueError(f"{path}: labels outside [0, 255]")
+        arr = arr.astype(np.uint8)
+    return np.ascontiguousarray(arr)
+
+
+def evaluate_files(true_path, pred_path, num_classes, **kwargs):
+    """Score one predicted label volume against its ground truth, both on disk: reads the two files and runs
+    ``suite.evaluate_host`` (chunked, copy/compute overlapped).  Keyword arguments go to ``evaluate_host``."""
+    from . import suite
+    yt, yp = read_labels(true_path), read_labels(pred_path)
+    if yt.shape != yp.shape:
+        raise ValueError(f"shape mismatch: {yt.shape} vs {yp.shape}")
+    return suite.evaluate_host(yt, yp, num_classes, **kwargs)

@@ -158,6 +158,26 @@ def boundary_error(bnd_true, bnd_pred):
     return sq, ab
 
 
+def labels_from_boundaries(boundaries, height):
+    """Boundary rows ``[N, Kb, W]`` (int or float, CUDA) -> uint8 label maps ``[N, height, W]``:
+    ``label[i, y, x] = #{k : b_k(i, x) <= y}``.  The inverse of the label pass's boundary rows on layered maps;
+    this is how boundary-curve annotations (Duke ``manualLayers``, HC-MS control points, the soft rows of a layer
+    model) become inputs of the mask metrics.  Rows may be unsorted, out of range or NaN (= boundary absent)."""
+    if not isinstance(boundaries, torch.Tensor) or not boundaries.is_cuda or boundaries.dim() != 3:
+        raise TypeError("expected a CUDA tensor [N, Kb, W]")
+    n, kb, w = boundaries.shape
+    if kb > 15:
+        raise ValueError("at most 15 boundaries (16 classes)")
+    if boundaries.is_floating_point():
+        b, dt = boundaries.to(torch.float32).contiguous(), _lib.DTYPE_F32
+    else:
+        b, dt = boundaries.to(torch.int32).contiguous(), _lib.DTYPE_I32
+    out = torch.empty((n, int(height), w), dtype=torch.uint8, device=b.device)
+    with torch.cuda.device(b.device):
+        _lib.call("octm_labels_from_boundaries", _ptr(b), dt, n, kb, int(height), w, _ptr(out), _stream())
+    return out
+
+
 def boundary_metrics(bnd_true, bnd_pred):
     """``mean_squared_error`` / ``root_mean_squared_error`` / ``mad`` of the reference applied to every
     boundary row: dict of float64 ``[N, Kb]`` CUDA tensors (reference: PixelError_based_metrics.py:14-35,
