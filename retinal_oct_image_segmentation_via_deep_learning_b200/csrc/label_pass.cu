@@ -570,14 +570,19 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
 // the joint code (t, p) comes in long RUNS (a column stays inside a layer for many rows): only a run's length
 // is accumulated per pixel; when the code changes the run goes into the warp's shared-memory confusion
 // histogram (one atomic per run, not per pixel) and into the thread's own per-class column counters.
-__global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams prm) {
+__global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams prm, const int strips) {
     __shared__ uint32_t s_counts[8][256];                 // per-warp confusion histogram, code = t * 16 + p
     __shared__ unsigned short s_cls[2][16][256];          // per-thread class counts of the current column
     __shared__ unsigned long long s_sq[16], s_abs[16], s_thick[16];
     __shared__ uint32_t s_first[2][16];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int H = prm.H, W = prm.W, K = prm.K, nthr = K - 1;
-    for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+    // strips > 1 (few items): a CTA takes 256 columns of an item and adds its share to zero-initialised outputs
+    const long long jobs = prm.n_items * strips;
+    for (long long job = blockIdx.x; job < jobs; job += gridDim.x) {
+        const long long item = job / strips;
+        const int xbeg = strips > 1 ? static_cast<int>(job % strips) * 256 : 0;
+        const int xend = strips > 1 ? min(W, xbeg + 256) : W;
         for (int i = tid; i < 8 * 256; i += 256) (&s_counts[0][0])[i] = 0;
         if (tid < 16) s_sq[tid] = s_abs[tid] = s_thick[tid] = 0;
         if (tid < 32) (&s_first[0][0])[tid] = OCTM_NO_SEED;
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
         for (int j = 0; j < 15; ++j) acc_sq[j] = acc_abs[j] = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc_th[j] = 0;
-        for (int x = tid; x < W; x += 256) {
+        for (int x = xbeg + tid; x < xend; x += 256) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) s_cls[0][c][tid] = s_cls[1][c][tid] = 0;
             uint32_t seen_t = 0, seen_p = 0;     // raster index grows with y inside one column
@@ -672,15 +677,28 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
                 const int code = (i / K) * 16 + (i % K);
                 unsigned long long sum = 0;
                 for (int w = 0; w < 8; ++w) sum += s_counts[w][code];
-                prm.counts[item * K * K + i] = sum;
+                if (strips == 1) prm.counts[item * K * K + i] = sum;
+                else if (sum) atomicAdd(prm.counts + item * K * K + i, sum);
             }
         }
-        if (tid < K && prm.thick != nullptr) prm.thick[item * K + tid] = static_cast<long long>(s_thick[tid]);
-        if (tid < nthr && prm.bsq != nullptr) prm.bsq[item * nthr + tid] = static_cast<long long>(s_sq[tid]);
-        if (tid < nthr && prm.babs != nullptr) prm.babs[item * nthr + tid] = static_cast<long long>(s_abs[tid]);
+        if (strips == 1) {
+            if (tid < K && prm.thick != nullptr) prm.thick[item * K + tid] = static_cast<long long>(s_thick[tid]);
+            if (tid < nthr && prm.bsq != nullptr) prm.bsq[item * nthr + tid] = static_cast<long long>(s_sq[tid]);
+            if (tid < nthr && prm.babs != nullptr) prm.babs[item * nthr + tid] = static_cast<long long>(s_abs[tid]);
+        } else {
+            if (tid < K && prm.thick != nullptr && s_thick[tid])
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.thick) + item * K + tid, s_thick[tid]);
+            if (tid < nthr && prm.bsq != nullptr && s_sq[tid])
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.bsq) + item * nthr + tid, s_sq[tid]);
+            if (tid < nthr && prm.babs != nullptr && s_abs[tid])
+                atomicAdd(reinterpret_cast<unsigned long long*>(prm.babs) + item * nthr + tid, s_abs[tid]);
+        }
         if (tid < 32 && prm.first_pos != nullptr) {
             const int m = tid >> 4, c = tid & 15;
-            if (c < K) prm.first_pos[(item * 2 + m) * K + c] = s_first[m][c];
+            if (c < K) {
+                if (strips == 1) prm.first_pos[(item * 2 + m) * K + c] = s_first[m][c];
+                else if (s_first[m][c] != OCTM_NO_SEED) atomicMin(prm.first_pos + (item * 2 + m) * K + c, s_first[m][c]);
+            }
         }
         __syncthreads();
     }
@@ -824,8 +842,22 @@ static int dispatch_np(const LabelPassParams& p, cudaStream_t stream) {
 }
 
 static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
-    long long grid = p.n_items < 148 * 8 ? p.n_items : 148 * 8;
-    label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p);
+    // few items: one CTA per 256-column strip, partial results joined by atomics on zero-initialised outputs
+    const long long resident = static_cast<long long>(sm_count()) * 8;
+    const int strips = p.n_items < resident && p.W > 256 ? (p.W + 255) / 256 : 1;
+    if (strips > 1) {
+        const size_t n = static_cast<size_t>(p.n_items), k = static_cast<size_t>(p.K);
+        bool ok = true;
+        if (p.counts) ok = ok && cudaMemsetAsync(p.counts, 0, n * k * k * 8, stream) == cudaSuccess;
+        if (p.thick) ok = ok && cudaMemsetAsync(p.thick, 0, n * k * 8, stream) == cudaSuccess;
+        if (p.bsq) ok = ok && cudaMemsetAsync(p.bsq, 0, n * (k - 1) * 8, stream) == cudaSuccess;
+        if (p.babs) ok = ok && cudaMemsetAsync(p.babs, 0, n * (k - 1) * 8, stream) == cudaSuccess;
+        if (p.first_pos) ok = ok && cudaMemsetAsync(p.first_pos, 0xff, n * 2 * k * 4, stream) == cudaSuccess;
+        if (!ok) return fail(OCTM_ERR_LAUNCH, "memset of the label-pass outputs failed");
+    }
+    long long grid = p.n_items * strips;
+    if (grid > resident) grid = resident;
+    label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p, strips);
     return check_launch("label_pass_generic");
 }
 

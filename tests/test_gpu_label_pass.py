@@ -70,7 +70,7 @@ def test_fast_kernel_layered_and_random(cuda, shape):
     _check(yt, yp, k, cuda)
 
 
-@pytest.mark.parametrize("shape", [(2, 33, 50, 16), (3, 17, 23, 2), (1, 496, 1024, 10), (2, 5, 7, 9), (1, 1, 1, 2),
+@pytest.mark.parametrize("shape", [(2, 33, 50, 16), (3, 17, 23, 2), (1, 496, 1024, 10), (2, 21, 300, 12), (2, 5, 7, 9), (1, 1, 1, 2),
                                    (2, 64, 96, 11)])
 def test_generic_kernel(cuda, shape):
     """Ragged widths and K > 8 go through the generic kernel."""
