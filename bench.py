@@ -195,7 +195,7 @@ def run_b200(args):
     _lib.load()
 
     n = args.items
-    yt, yp = synth.layered_pair_device(n, H, W, K, seed=4004 + rank, device=dev)
+    yt, yp = synth.layered_pair_device(n, H, W, K, seed=4004 + rank, device=dev, noise=args.noise)
     torch.cuda.synchronize()
 
     timers = {}
@@ -322,7 +322,8 @@ def run_b200(args):
             "metric": "bscans_per_sec_full_metric_suite", "value": value, "unit": "B-scans/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "items_per_gpu": n, "height": H, "width": W, "num_classes": K,
+            "config": {"workload": WORKLOAD + (f", {args.noise:g} of the predicted pixels randomised" if args.noise else ""),
+                       "items_per_gpu": n, "height": H, "width": W, "num_classes": K,
                        "contours": not args.no_contours, "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2"
                        % (n * BYTES_PER_BSCAN / 1e9), "sharding": f"items x{world}, one NCCL all-reduce of totals",
                        "results": "left in HBM during the timed region; every step's dataset totals are read back and compared after it"},
@@ -341,6 +342,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--items", type=int, default=16384, help="B-scans per GPU per step")
+    ap.add_argument("--noise", type=float, default=0.0,
+                    help="fraction of predicted pixels replaced by a random class (default 0: the contract's clean layered maps)")
     ap.add_argument("--e2e-items", type=int, default=4096)
     ap.add_argument("--no-contours", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
