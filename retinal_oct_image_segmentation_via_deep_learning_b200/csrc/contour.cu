@@ -269,11 +269,12 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
                                 static_cast<unsigned>(hl - 1) <= hm && static_cast<unsigned>(hr - 1) <= hm;
             if (!__all_sync(0xffffffffu, !valid || inside)) { ok = false; break; }
             // windows of the two columns as 32-bit pixel offsets (H * W < 2^31 on this path)
-            const int loa = (min(hl, min(ha, hb)) - 1) * W, hia = max(hl, max(ha, hb)) * W;
-            const int lob = (min(ha, min(hb, hr)) - 1) * W, hib = max(ha, max(hb, hr)) * W;
+            const int rla = min(hl, min(ha, hb)) - 1, rha = max(hl, max(ha, hb));
+            const int rlb = min(ha, min(hb, hr)) - 1, rhb = max(ha, max(hb, hr));
+            const int loa = rla * W, hia = rha * W, lob = rlb * W, hib = rhb * W;
             const int olo = min(loa, lob), ohi = max(hia, hib), oha = ha * W, ohb = hb * W;
             const uint8_t* colp = L + xc;
-            const int nrows = __reduce_max_sync(0xffffffffu, valid ? (ohi - olo) / W + 1 : 0);
+            const int nrows = __reduce_max_sync(0xffffffffu, valid ? max(rha, rhb) - min(rla, rlb) + 1 : 0);
             for (int u0 = 0; u0 < nrows; u0 += 4) {        // four rows in flight, two pixels each
                 int off[4];
                 uint32_t px[4];
