@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {              // past the window: its last row again (harmless)
                     off[u] = min(olo + (u0 + u) * W, ohi);
-                    px[u] = __ldg(reinterpret_cast<const unsigned short*>(colp + off[u]));
+                    px[u] = __ldg(reinterpret_cast<const unsigned short*>(colp + static_cast<uint32_t>(off[u])));
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -299,19 +299,20 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
                 const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += up;
             }
-            uint32_t pos = base + incl - cnt;
+            const uint32_t pos = base + incl - cnt;
             base += __shfl_sync(0xffffffffu, incl, 31);
             if (base > cap) { ok = false; break; }         // too long: the walk flags the overflow
             if (valid) {
                 const uint32_t x2 = 2u * static_cast<uint32_t>(x);
                 const uint32_t ua = static_cast<uint32_t>(ha), ub = static_cast<uint32_t>(hb), uw = static_cast<uint32_t>(W);
                 minkey = min(minkey, min(ua * uw + static_cast<uint32_t>(x), ub * uw + static_cast<uint32_t>(x) + 1u));
-                out[pos++] = (static_cast<uint32_t>(2 * ha - 1) << 16) | x2;
-                const int ra = min(ha, hb);
-                for (int t = 0; t < da; ++t) out[pos++] = (static_cast<uint32_t>(2 * (ra + t)) << 16) | (x2 + 1u);
-                out[pos++] = (static_cast<uint32_t>(2 * hb - 1) << 16) | (x2 + 2u);
-                const int rb = min(hb, hr);
-                for (int t = 0; t < db; ++t) out[pos++] = (static_cast<uint32_t>(2 * (rb + t)) << 16) | (x2 + 3u);
+                uint32_t* o = out + pos;
+                *o++ = (static_cast<uint32_t>(2 * ha - 1) << 16) | x2;
+                uint32_t va = (static_cast<uint32_t>(2 * min(ha, hb)) << 16) | (x2 + 1u);
+                for (int t = 0; t < da; ++t, va += 2u << 16) *o++ = va;
+                *o++ = (static_cast<uint32_t>(2 * hb - 1) << 16) | (x2 + 2u);
+                uint32_t vb = (static_cast<uint32_t>(2 * min(hb, hr)) << 16) | (x2 + 3u);
+                for (int t = 0; t < db; ++t, vb += 2u << 16) *o++ = vb;
             }
         }
         if (ok) ok = !__any_sync(0xffffffffu, bad) && __reduce_min_sync(0xffffffffu, minkey) == seed;
