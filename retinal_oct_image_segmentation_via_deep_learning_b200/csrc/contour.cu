@@ -975,6 +975,83 @@ __device__ __forceinline__ void coop_scan_range(const int4* src, int a, int len,
     }
 }
 
+// The search proper: every warp takes the query chunks c = warp, warp + 8, ... of the unit.  COUNT: the minima go
+// to the shared-memory counters; STORE: they are written to the d2 scratch.  Instantiated three times so that the
+// usual pass (count, do not store) carries neither the store's address arithmetic nor its registers.
+// Chunks are dealt out statically: a shared counter balances the warps slightly better but costs more than it
+// saves (measured 3.96 vs 3.84 ms).
+template <bool COUNT, bool STORE>
+__device__ __forceinline__ void column_chunks(const int4* src, const uint32_t* col, const uint32_t* vq, uint32_t* dq,
+                                              int ns, int nq, int ncol, int nchunks, int warp, int lane, uint32_t* s_bins,
+                                              uint32_t& run_max, bool& run_bad) {
+    constexpr int kWarps = kColThreads / 32;
+#pragma unroll 1
+    for (int c = warp; c < nchunks; c += kWarps) {
+        // lane l holds the consecutive queries c * 32 Q + l Q .. + Q - 1 (tail lanes repeat the last query)
+        const int j0 = (c * 32 + lane) * kColQ;
+        int qx[kColQ], cy[kColQ], cx[kColQ], qn[kColQ], bm[kColQ];
+#pragma unroll
+        for (int q = 0; q < kColQ; ++q) {
+            const uint32_t v = vq[min(j0 + q, nq - 1)];
+            const int qy = v >> 16;
+            qx[q] = v & 0xffff;
+            cy[q] = -2 * qy; cx[q] = -2 * qx[q]; qn[q] = qy * qy + qx[q] * qx[q];
+            bm[q] = 0x3fffffff;                // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
+        }
+        // Consecutive polyline vertices are at most 2 columns apart; a larger step is the seam between the
+        // forward and the backward run of a walked open contour (or the closing repeat): the queries before
+        // and after it get their own column span, so that no span covers the columns in between.
+        // first = index (in this chunk's 32 Q queries) of the first query after the seam.
+        int first = 32 * kColQ;
+        {
+            const int qprev = __shfl_up_sync(0xffffffffu, qx[kColQ - 1], 1);
+#pragma unroll
+            for (int q = 0; q < kColQ; ++q) {
+                const bool jump = q == 0 ? (lane > 0 && abs(qx[0] - qprev) > 2) : abs(qx[q] - qx[q - 1]) > 2;
+                const uint32_t m = __ballot_sync(0xffffffffu, jump);
+                if (m) first = min(first, (__ffs(m) - 1) * kColQ + q);
+            }
+        }
+        for (int part = 0;; ++part) {          // part 0: queries before `first`, part 1: the rest
+            int x0 = 0x7fffffff, x1 = -1, bmine = 0;
+#pragma unroll
+            for (int q = 0; q < kColQ; ++q) {
+                const bool mine = ((lane * kColQ + q) < first) == (part == 0);
+                x0 = min(x0, mine ? qx[q] : 0x7fffffff);
+                x1 = max(x1, mine ? qx[q] : -1);
+            }
+            x0 = min(group_min(x0), ncol - 1);
+            x1 = min(group_max(x1), ncol - 1);
+            const bool has = x1 >= 0;          // this group has queries in this part
+            const int lo = has ? static_cast<int>(col[x0]) : 0, hi = has ? static_cast<int>(col[x1 + 1]) : 0;
+            coop_scan_range(src, lo, hi - lo, ns + 3, cy, cx, bm);
+#pragma unroll
+            for (int q = 0; q < kColQ; ++q) {
+                const bool mine = ((lane * kColQ + q) < first) == (part == 0);
+                bmine = max(bmine, mine ? bm[q] + qn[q] : 0);
+            }
+            const int bmax = group_max(bmine);
+            // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
+            // (the approximate square root is exact enough below 2^20; real distances are below 2^29)
+            float rf;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(static_cast<float>(bmax)));
+            const int r = bmax >= 0x3fffffff ? ncol : static_cast<int>(rf) + (bmax >= (1 << 20) ? 1 : 0);
+            const int fl = has ? static_cast<int>(col[max(x0 - r, 0)]) : 0;
+            const int fr = has ? static_cast<int>(col[min(x1 + r, ncol - 1) + 1]) : 0;
+            coop_scan_range(src, fl, lo - fl, ns + 3, cy, cx, bm);
+            coop_scan_range(src, hi, fr - hi, ns + 3, cy, cx, bm);
+            if (part == 1 || first == 32 * kColQ) break;
+        }
+        #pragma unroll
+        for (int q = 0; q < kColQ; ++q) {
+            const int bestd = bm[q] + qn[q];
+            const bool valid = j0 + q < nq;
+            if (STORE && valid) dq[j0 + q] = static_cast<uint32_t>(bestd);
+            if (COUNT) count_minima(bestd, valid, lane, s_bins, run_max, run_bad);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_kernel(const ColumnParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t s_bins[kCountBins / 2];
@@ -1099,82 +1176,19 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
         // The final minima are counted (16-bit counters, one per even value) instead of stored; a unit with a value
         // the counters cannot hold repeats the search in store mode and is left to distance_select_kernel.
         bool count = nq <= 0xffff;
-        uint32_t run_max = 0;
-        bool run_bad = false;
-        for (;;) {
-            // chunks are dealt out statically: a shared counter balances the warps slightly better but costs more
-            // than it saves (measured 3.96 vs 3.84 ms)
-#pragma unroll 1
-            for (int c = warp; c < nchunks; c += kWarps) {
-                // lane l holds the consecutive queries c * 32 Q + l Q .. + Q - 1 (tail lanes repeat the last query)
-                const int j0 = (c * 32 + lane) * kColQ;
-                int qx[kColQ], cy[kColQ], cx[kColQ], qn[kColQ], bm[kColQ];
-#pragma unroll
-                for (int q = 0; q < kColQ; ++q) {
-                    const uint32_t v = vq[min(j0 + q, nq - 1)];
-                    const int qy = v >> 16;
-                    qx[q] = v & 0xffff;
-                    cy[q] = -2 * qy; cx[q] = -2 * qx[q]; qn[q] = qy * qy + qx[q] * qx[q];
-                    bm[q] = 0x3fffffff;                // best of s.y * cy + s.x * cx + |s|^2 ( = d^2 - |q|^2 )
-                }
-                // Consecutive polyline vertices are at most 2 columns apart; a larger step is the seam between the
-                // forward and the backward run of a walked open contour (or the closing repeat): the queries before
-                // and after it get their own column span, so that no span covers the columns in between.
-                // first = index (in this chunk's 32 Q queries) of the first query after the seam.
-                int first = 32 * kColQ;
-                {
-                    const int qprev = __shfl_up_sync(0xffffffffu, qx[kColQ - 1], 1);
-#pragma unroll
-                    for (int q = 0; q < kColQ; ++q) {
-                        const bool jump = q == 0 ? (lane > 0 && abs(qx[0] - qprev) > 2) : abs(qx[q] - qx[q - 1]) > 2;
-                        const uint32_t m = __ballot_sync(0xffffffffu, jump);
-                        if (m) first = min(first, (__ffs(m) - 1) * kColQ + q);
-                    }
-                }
-                for (int part = 0;; ++part) {          // part 0: queries before `first`, part 1: the rest
-                    int x0 = 0x7fffffff, x1 = -1, bmine = 0;
-#pragma unroll
-                    for (int q = 0; q < kColQ; ++q) {
-                        const bool mine = ((lane * kColQ + q) < first) == (part == 0);
-                        x0 = min(x0, mine ? qx[q] : 0x7fffffff);
-                        x1 = max(x1, mine ? qx[q] : -1);
-                    }
-                    x0 = min(group_min(x0), ncol - 1);
-                    x1 = min(group_max(x1), ncol - 1);
-                    const bool has = x1 >= 0;          // this group has queries in this part
-                    const int lo = has ? static_cast<int>(col[x0]) : 0, hi = has ? static_cast<int>(col[x1 + 1]) : 0;
-                    coop_scan_range(src, lo, hi - lo, ns + 3, cy, cx, bm);
-#pragma unroll
-                    for (int q = 0; q < kColQ; ++q) {
-                        const bool mine = ((lane * kColQ + q) < first) == (part == 0);
-                        bmine = max(bmine, mine ? bm[q] + qn[q] : 0);
-                    }
-                    const int bmax = group_max(bmine);
-                    // columns that can still hold a nearer vertex: dx^2 < best  =>  dx <= isqrt(best - 1) <= r
-                    // (the approximate square root is exact enough below 2^20; real distances are below 2^29)
-                    float rf;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(static_cast<float>(bmax)));
-                    const int r = bmax >= 0x3fffffff ? ncol : static_cast<int>(rf) + (bmax >= (1 << 20) ? 1 : 0);
-                    const int fl = has ? static_cast<int>(col[max(x0 - r, 0)]) : 0;
-                    const int fr = has ? static_cast<int>(col[min(x1 + r, ncol - 1) + 1]) : 0;
-                    coop_scan_range(src, fl, lo - fl, ns + 3, cy, cx, bm);
-                    coop_scan_range(src, hi, fr - hi, ns + 3, cy, cx, bm);
-                    if (part == 1 || first == 32 * kColQ) break;
-                }
-                const bool store = !count || prm.keep_d2;
-#pragma unroll
-                for (int q = 0; q < kColQ; ++q) {
-                    const int bestd = bm[q] + qn[q];
-                    const bool valid = j0 + q < nq;
-                    if (store && valid) dq[j0 + q] = static_cast<uint32_t>(bestd);
-                    if (count) count_minima(bestd, valid, lane, s_bins, run_max, run_bad);
-                }
-            }
-            if (!count) break;
+        if (count) {
+            uint32_t run_max = 0;
+            bool run_bad = false;
+            if (prm.keep_d2) column_chunks<true, true>(src, col, vq, dq, ns, nq, ncol, nchunks, warp, lane, s_bins, run_max, run_bad);
+            else column_chunks<true, false>(src, col, vq, dq, ns, nq, ncol, nchunks, warp, lane, s_bins, run_max, run_bad);
             publish_counts(run_max, run_bad, lane, &s_vmax, &s_big);
             __syncthreads();                           // counters, s_vmax, s_big complete
-            if (s_big == 0) break;
-            count = false;                             // CTA-uniform: search again, storing
+            count = s_big == 0;                        // CTA-uniform
+        }
+        if (!count) {                                  // search (again), storing
+            uint32_t run_max = 0;
+            bool run_bad = false;
+            column_chunks<false, true>(src, col, vq, dq, ns, nq, ncol, nchunks, warp, lane, s_bins, run_max, run_bad);
         }
         synced = count;                                // the barrier above also ends every warp's use of the tables
         if (warp != 0) continue;
