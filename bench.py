@@ -32,8 +32,8 @@ H, W, K = 496, 512, 8
 BYTES_PER_BSCAN = 2 * H * W                      # algorithmic (compulsory) label bytes, SURVEY.md 8(d)
 WORKLOAD = "cfg4: full metric suite, synthetic layered 496x512 B-scans, 8 classes"
 # DRAM traffic of label_pass_fast per B-scan from the ncu --set full capture of this workload
-# (profiles/r1_v9_ncu_summary.md: dram__bytes_read 1.041600 GB + dram__bytes_write 11.678 MB for 2048 B-scans)
-NCU_TRAFFIC_BYTES_PER_BSCAN = (1.041600e9 + 11.677952e6) / 2048
+# (profiles/r1_v10_ncu_summary.md: dram__bytes_read 1.041599 GB + dram__bytes_write 11.639 MB for 2048 B-scans)
+NCU_TRAFFIC_BYTES_PER_BSCAN = (1.041599e9 + 11.638528e6) / 2048
 
 
 def _peaks():
@@ -268,7 +268,7 @@ def run_b200(args):
         achieved = n * BYTES_PER_BSCAN / (lp_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "label_pass_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": n * NCU_TRAFFIC_BYTES_PER_BSCAN if not args.no_contours else None,
-                    "traffic_source": "ncu dram__bytes_read+write per B-scan (profiles/r1_v9_ncu_summary.md) x items per launch",
+                    "traffic_source": "ncu dram__bytes_read+write per B-scan (profiles/r1_v10_ncu_summary.md) x items per launch",
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": n * BYTES_PER_BSCAN, "ms_per_launch": lp_ms,
                     "suite_compulsory_gbs_per_gpu": n * BYTES_PER_BSCAN * args.steps / (ms / 1e3) / 1e9}
@@ -292,7 +292,7 @@ def run_b200(args):
             suite.evaluate_host(ht, hp, K, contours=not args.no_contours, device=dev).metrics()
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 6))
         d2h = 0
         for _ in range(e2e_steps):
             r = suite.evaluate_host(ht, hp, K, contours=not args.no_contours, device=dev)
