@@ -254,9 +254,12 @@ OCTM_API int octm_unpack_nibbles_u8(const uint8_t* packed, int64_t n_labels, uin
  *                                         boundary rows b_k (may be NULL)
  *   totals           double [octm_totals_len(K)] = this batch's dataset-level partial sums in the
  *                    layout [n_items | cm K*K | thick K | bnd_sq K-1 | bnd_abs K-1 | contour_items K |
- *                    sum hd K | sum hd95 K | sum assd K | max hd K | OR of contour flags] (may be NULL);
- *                    integer fields are exact below 2^53; this is the vector the multi-GPU
- *                    all-reduce sums. */
+ *                    sum hd K | sum hd95 K | sum assd K | n_overflow_items | n_bad_label_items |
+ *                    max hd K | OR of contour flags] (may be NULL; written for n_items == 0 as well);
+ *                    integer fields are exact below 2^53.  The first octm_totals_sum_len(K) entries are what
+ *                    the multi-GPU all-reduce sums: n_overflow_items = items with an OCTM_CF_*_OVERFLOW flag,
+ *                    n_bad_label_items = items whose confusion counts do not add up to H * W (the label pass
+ *                    drops every pixel pair with a label >= K instead of aliasing it into another class). */
 #define OCTM_M_ACCURACY 0
 #define OCTM_M_SENSITIVITY 1
 #define OCTM_M_CM_PRECISION 2
@@ -276,6 +279,7 @@ OCTM_API int octm_unpack_nibbles_u8(const uint8_t* packed, int64_t n_labels, uin
 #define OCTM_NUM_CLASS_METRICS 16
 
 OCTM_API int octm_totals_len(int num_classes);
+OCTM_API int octm_totals_sum_len(int num_classes);
 OCTM_API int octm_derive_metrics(const uint64_t* counts, const int64_t* thick_absdiff, const int64_t* bnd_sq,
                         const int64_t* bnd_abs, const uint32_t* n_pts, const uint32_t* max_sq,
                         const uint32_t* p95_sq, const double* sum_dist, const uint32_t* contour_flags,

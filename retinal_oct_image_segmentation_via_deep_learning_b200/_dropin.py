@@ -54,9 +54,18 @@ def binary_counts(y_true, y_pred):
 
 
 def is_binary_like(a):
+    """True when ``a`` really is a 0/1 mask: bool dtype, or uint8 whose maximum is <= 1 (checked).  Only such
+    pairs may take the confusion-kernel shortcut of mean_squared_error / root_mean_squared_error / mad; any
+    other integer array (multi-class label maps, uint8 images, boundary rows stored as uint8) goes through
+    ``error_sums``, which reproduces the reference's ``astype(float)`` differences for any values."""
     if isinstance(a, torch.Tensor):
-        return a.dtype in (torch.bool, torch.uint8)
-    return np.asarray(a).dtype in (np.bool_, np.uint8)
+        if a.dtype == torch.bool:
+            return True
+        return a.dtype == torch.uint8 and (a.numel() == 0 or int(a.max()) <= 1)
+    arr = np.asarray(a)
+    if arr.dtype == np.bool_:
+        return True
+    return arr.dtype == np.uint8 and (arr.size == 0 or int(arr.max()) <= 1)
 
 
 def error_sums(y_true, y_pred):

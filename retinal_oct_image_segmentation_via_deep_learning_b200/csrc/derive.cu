@@ -101,7 +101,12 @@ __global__ void __launch_bounds__(128) derive_kernel(const DeriveParams p) {
 // Dataset-level partial sums of this rank, one CTA per output element, fixed reduction order
 // (thread-strided partials, then a shuffle/shared-memory tree): bit-reproducible run to run.
 // Layout (mirrors dist.local_partials): [n_items | cm K*K | thick K | bsq K-1 | babs K-1 |
-//   contour_items K | sum hd K | sum hd95 K | sum assd K | max hd K | OR of contour flags]
+//   contour_items K | sum hd K | sum hd95 K | sum assd K | n_overflow_items | n_bad_label_items |
+//   max hd K | OR of contour flags]
+// The first octm_totals_sum_len(K) entries are SUM-reducible across ranks; n_overflow_items counts the items
+// with a contour-overflow flag and n_bad_label_items those whose confusion counts do not add up to H * W (the
+// label pass drops pixels whose label is >= K), so that every rank of a multi-GPU job takes the same decision
+// (retry / raise) from the reduced vector.
 struct TotalsParams {
     const unsigned long long* counts;
     const long long* thick;
@@ -110,6 +115,7 @@ struct TotalsParams {
     const double* cls;         // [n][K][OCTM_NUM_CLASS_METRICS]
     const uint32_t* flags;     // [n][K] or null
     long long n_items;
+    long long item_px;         // H * W
     int K;
     double* out;
 };
@@ -119,7 +125,8 @@ __global__ void __launch_bounds__(256) totals_kernel(const TotalsParams p) {
     __shared__ long long s_i[8];
     const int K = p.K, e = blockIdx.x, tid = threadIdx.x;
     const int o_cm = 1, o_th = o_cm + K * K, o_bs = o_th + K, o_ba = o_bs + K - 1, o_nv = o_ba + K - 1;
-    const int o_hd = o_nv + K, o_h95 = o_hd + K, o_as = o_h95 + K, o_mx = o_as + K, o_fl = o_mx + K;
+    const int o_hd = o_nv + K, o_h95 = o_hd + K, o_as = o_h95 + K, o_ov = o_as + K, o_bad = o_ov + 1, o_mx = o_bad + 1,
+              o_fl = o_mx + K;
     long long isum = 0;
     double dsum = 0.0, dmax = -1.0;
     bool is_int = true, is_max = false;
@@ -133,11 +140,19 @@ __global__ void __launch_bounds__(256) totals_kernel(const TotalsParams p) {
         else if (e < o_ba) isum += p.bsq ? p.bsq[i * (K - 1) + (e - o_bs)] : 0;
         else if (e < o_nv) isum += p.babs ? p.babs[i * (K - 1) + (e - o_ba)] : 0;
         else if (e < o_hd) { const double v = p.cls[(i * K + (e - o_nv)) * OCTM_NUM_CLASS_METRICS + OCTM_M_HAUSDORFF]; isum += (v == v) ? 1 : 0; }
-        else if (e < o_mx) {
+        else if (e < o_ov) {
             is_int = false;
             const int which = (e - o_hd) / K, c = (e - o_hd) % K;
             const double v = p.cls[(i * K + c) * OCTM_NUM_CLASS_METRICS + OCTM_M_HAUSDORFF + which];
             if (v == v) dsum += v;
+        } else if (e == o_ov) {
+            uint32_t f = 0;
+            for (int c = 0; c < K; ++c) f |= p.flags ? p.flags[i * K + c] : 0;
+            isum += (f & (OCTM_CF_TRUE_OVERFLOW | OCTM_CF_PRED_OVERFLOW)) ? 1 : 0;
+        } else if (e == o_bad) {
+            unsigned long long px = 0;
+            for (int c = 0; c < K * K; ++c) px += p.counts[i * K * K + c];
+            isum += px != static_cast<unsigned long long>(p.item_px) ? 1 : 0;
         } else if (e < o_fl) {
             is_int = false; is_max = true;
             const double v = p.cls[(i * K + (e - o_mx)) * OCTM_NUM_CLASS_METRICS + OCTM_M_HAUSDORFF];
@@ -171,7 +186,12 @@ __global__ void __launch_bounds__(256) totals_kernel(const TotalsParams p) {
 
 extern "C" int octm_totals_len(int num_classes) {
     const int K = num_classes;
-    return 1 + K * K + K + 2 * (K - 1) + 5 * K + 1;
+    return 1 + K * K + K + 2 * (K - 1) + 4 * K + 2 + K + 1;
+}
+
+extern "C" int octm_totals_sum_len(int num_classes) {
+    const int K = num_classes;
+    return 1 + K * K + K + 2 * (K - 1) + 4 * K + 2;
 }
 
 extern "C" int octm_derive_metrics(const uint64_t* counts, const int64_t* thick_absdiff, const int64_t* bnd_sq,
@@ -181,8 +201,7 @@ extern "C" int octm_derive_metrics(const uint64_t* counts, const int64_t* thick_
                                    double* boundary_metrics, double* totals, void* stream) {
     if (n_items < 0 || num_classes < 2 || num_classes > OCTM_MAX_CLASSES || W < 1 || H < 1)
         return octm::fail(OCTM_ERR_INVALID, "bad shape");
-    if (n_items == 0) return OCTM_OK;
-    if (!counts || !class_metrics) return octm::fail(OCTM_ERR_INVALID, "counts and class_metrics are required");
+    if (n_items > 0 && (!counts || !class_metrics)) return octm::fail(OCTM_ERR_INVALID, "counts and class_metrics are required");
     if (n_pts && (!max_sq || !p95_sq || !sum_dist)) return octm::fail(OCTM_ERR_INVALID, "incomplete contour inputs");
     if (boundary_metrics && (!bnd_sq || !bnd_abs)) return octm::fail(OCTM_ERR_INVALID, "boundary sums missing");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -190,10 +209,13 @@ extern "C" int octm_derive_metrics(const uint64_t* counts, const int64_t* thick_
                          reinterpret_cast<const long long*>(bnd_sq), reinterpret_cast<const long long*>(bnd_abs), n_pts, max_sq,
                          p95_sq, sum_dist, n_items, H, W, num_classes, class_metrics, boundary_metrics};
     const long long threads = n_items * num_classes;
-    octm::derive_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(p);
-    if (int e = octm::check_launch("derive_kernel")) return e;
-    if (totals != nullptr) {
-        octm::TotalsParams t{p.counts, p.thick, p.bsq, p.babs, class_metrics, contour_flags, n_items, num_classes, totals};
+    if (n_items > 0) {
+        octm::derive_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(p);
+        if (int e = octm::check_launch("derive_kernel")) return e;
+    }
+    if (totals != nullptr) {       // also for an empty batch: n_items 0, sums 0, maxima -1, flags 0
+        octm::TotalsParams t{p.counts, p.thick, p.bsq, p.babs, class_metrics, contour_flags, n_items,
+                             static_cast<long long>(H) * W, num_classes, totals};
         octm::totals_kernel<<<octm_totals_len(num_classes), 256, 0, s>>>(t);
         if (int e = octm::check_launch("totals_kernel")) return e;
     }

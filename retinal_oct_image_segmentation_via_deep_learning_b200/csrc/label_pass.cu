@@ -277,6 +277,7 @@ struct StageConsts {
     uint4* queue;
     unsigned short* totals;
     uint32_t* first_tab;
+    uint32_t* bad;                // set when a label with bits above the 3-bit class range shows up
 };
 
 // One ring stage (rows x strip) of one consumer warp.  Each pass of the loop takes 4 rows: lanes 0-15 rows
@@ -309,14 +310,20 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
         if (CONF || SEEDS) {
             uint4 j = make_uint4(tA.x * 8u + pA.x, tA.y * 8u + pA.y, tB.x * 8u + pB.x, tB.y * 8u + pB.y);
             const uint32_t b = prmt(j.x, 0, 0);
+            // labels >= 8 (outside what the 6-bit joint code can hold) must never alias a valid code: OR of all 16
+            // label pairs, bits 3-7 of every byte (the pad label 8 of missing rows / columns is masked out below)
+            const uint32_t high = ((tA.x | tA.y | tB.x) | (tB.y | pA.x | pA.y) | (pB.x | pB.y)) & 0xf8f8f8f8u;
             // uniform lane: all 16 pixel pairs share one joint code (padded lanes never take this path)
-            const bool uni = FULL && (((j.x ^ b) | (j.y ^ b)) | ((j.z ^ b) | (j.w ^ b))) == 0;
+            const bool uni = FULL && ((((j.x ^ b) | (j.y ^ b)) | ((j.z ^ b) | (j.w ^ b))) | high) == 0;
             // uniform row pairs come in long runs of one joint code (a lane stays inside a layer for many rows): the
             // run length lives in a register and reaches the lane's private histogram column when the code changes
             const bool changed = uni && b != ls.last_b;
             if (uni && !changed) ls.run += 16u;
             const bool mixed_lane = FULL ? !uni : (va || vb);
             if (__any_sync(0xffffffffu, mixed_lane || changed)) {
+                if (CONF && (FULL ? high != 0 : ((va && ((tA.x | tA.y | pA.x | pA.y) & 0xf8f8f8f8u)) ||
+                                        (vb && ((tB.x | tB.y | pB.x | pB.y) & 0xf8f8f8f8u)))))
+                    *sc.bad = 1;                    // this warp's counts of the item are withheld (epilogue)
                 if (changed) {
                     if (CONF && ls.last_b != 0xffffffffu) hist_add(sc.hist_lane, ls.last_b & 0x3fu, ls.run);
                     ls.last_b = b;
@@ -384,6 +391,7 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     const uint32_t bars = smem_u32(wbase);                                  // full[s] at bars + 8 s
     const uint32_t ring_addr = bars + state_bytes;
     uint32_t* warp_first = reinterpret_cast<uint32_t*>(wbase + 128);        // [2][16] first raster position per class
+    uint32_t* warp_bad = reinterpret_cast<uint32_t*>(wbase + 64);           // a label >= 8 was met in this item
     if (lane == 0) {
         for (int s = 0; s < S; ++s) mbar_init_a(bars + 8 * s, 1);
         mbar_fence_init();
@@ -428,15 +436,14 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     sc.srow2 = 2u * srow; sc.srow4 = 4u * srow; sc.W2 = 2u * W; sc.W4 = 4u * W;
     sc.map_bytes = map_bytes; sc.one = prm.one; sc.all_classes = ((1u << K) - 1u) * 0x101u;
     sc.phase = phase; sc.lane = lane; sc.colv = colv;
-    sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.first_tab = warp_first;
+    sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.first_tab = warp_first; sc.bad = warp_bad;
     LaneState<NP> ls;
     uint32_t s = 0, ph = 0;
     for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
         ls.reset(COLS);
-        if (SEEDS) {
-            warp_first[lane] = OCTM_NO_SEED;
-            __syncwarp();
-        }
+        if (CONF && lane == 0) *warp_bad = 0;
+        if (SEEDS) warp_first[lane] = OCTM_NO_SEED;
+        __syncwarp();
 
         for (int r0 = 0; r0 < H; r0 += R) {
             const int rows = min(R, H - r0);
@@ -467,6 +474,10 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
             __syncwarp();
             if (static_cast<uint32_t>(lane) < left) drain_entry(hist_lane, queue[(ls.qhead + lane) & (kQueueCap - 1)]);
             __syncwarp();
+            // a label >= 8 may have aliased a valid joint code: withhold this warp's counts, so that the item's
+            // confusion matrix does not add up to H * W and the epilogue reports it (labels in [K, 8) are dropped
+            // by the t < K && pp < K test below: same effect)
+            const bool wbad = *warp_bad != 0;
             uint32_t* h32 = reinterpret_cast<uint32_t*>(hist);
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -482,7 +493,7 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
                 }
                 // this warp's share of cm[t][p] joins the other strips' in the (zero-initialised) output
                 const int t = code >> 3, pp = code & 7;
-                if ((lo + hi) && t < K && pp < K)
+                if ((lo + hi) && t < K && pp < K && !wbad && prm.counts != nullptr)
                     atomicAdd(prm.counts + (item * K + t) * K + pp, static_cast<unsigned long long>(lo + hi));
             }
         }
@@ -603,26 +614,28 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
             uint32_t seen_t = 0, seen_p = 0;     // raster index grows with y inside one column
             uint32_t run_code = 0xffffffffu, run = 0;
             auto flush = [&]() {
-                if (run) {
-                    const uint32_t t = run_code >> 4, p = run_code & 15u;
-                    atomicAdd(&s_counts[warp][run_code], run);
+                // a run with a label >= K is dropped (never aliased into another class): the item's counts then do
+                // not add up to H * W, which the epilogue reports
+                if (run && (run_code >> 8) < static_cast<uint32_t>(K) && (run_code & 255u) < static_cast<uint32_t>(K)) {
+                    const uint32_t t = run_code >> 8, p = run_code & 255u;
+                    atomicAdd(&s_counts[warp][t * 16u + p], run);
                     s_cls[0][t][tid] = static_cast<unsigned short>(s_cls[0][t][tid] + run);
                     s_cls[1][p][tid] = static_cast<unsigned short>(s_cls[1][p][tid] + run);
                 }
             };
 #pragma unroll 4
             for (int y = 0; y < H; ++y) {
-                const uint32_t t = bt[static_cast<long long>(y) * W + x] & 15u, p = bp[static_cast<long long>(y) * W + x] & 15u;
-                const uint32_t code = t * 16u + p;
+                const uint32_t t = bt[static_cast<long long>(y) * W + x], p = bp[static_cast<long long>(y) * W + x];
+                const uint32_t code = t * 256u + p;
                 if (code != run_code) {
                     flush();
                     run_code = code;
                     run = 0;
-                    if (!((seen_t >> t) & 1u)) {
+                    if (t < 16u && !((seen_t >> t) & 1u)) {
                         seen_t |= 1u << t;
                         atomicMin(&s_first[0][t], static_cast<uint32_t>(y * W + x));
                     }
-                    if (!((seen_p >> p) & 1u)) {
+                    if (p < 16u && !((seen_p >> p) & 1u)) {
                         seen_p |= 1u << p;
                         atomicMin(&s_first[1][p], static_cast<uint32_t>(y * W + x));
                     }

@@ -25,7 +25,8 @@ def shard_range(n_items, rank, world):
 
 
 def local_partials(ints, metrics, num_classes):
-    """Pack this rank's sums into one float64 vector (layout mirrored by ``unpack``)."""
+    """Pack this rank's sums into one float64 vector (layout mirrored by ``unpack`` and by the device-side
+    ``totals_kernel``: the SUM-reducible head of ``octm_derive_metrics``' totals)."""
     k = num_classes
     parts = [np.asarray([ints["confusion"].shape[0]], np.float64),
              ints["confusion"].astype(np.int64).sum(0).reshape(-1).astype(np.float64)]
@@ -41,11 +42,23 @@ def local_partials(ints, metrics, num_classes):
             parts.append(np.where(valid, metrics[name], 0.0).sum(0))
     else:
         parts += [np.zeros(k)] * 4
+    n_over = 0
+    if "contour_flags" in ints:
+        n_over = int(((np.asarray(ints["contour_flags"]).astype(np.int64) & 12) != 0).any(axis=1).sum())
+    n_bad = 0
+    if "item_pixels" in ints:
+        cm = ints["confusion"].astype(np.int64)
+        n_bad = int((cm.reshape(cm.shape[0], -1).sum(1) != int(ints["item_pixels"])).sum())
+    parts.append(np.asarray([n_over, n_bad], np.float64))
     vec = np.concatenate(parts)
+    _check_exact(vec, k)
+    return vec
+
+
+def _check_exact(vec, k):
     n_exact = 1 + k * k + k + 2 * (k - 1) + k
     if np.any(np.abs(vec[:n_exact]) >= _EXACT_LIMIT):
         raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")
-    return vec
 
 
 def unpack(vec, num_classes, width):
@@ -64,7 +77,9 @@ def unpack(vec, num_classes, width):
     bsq, bab = np.rint(take(k - 1)).astype(np.int64), np.rint(take(k - 1)).astype(np.int64)
     nvalid = np.rint(take(k)).astype(np.int64)
     s_hd, s_hd95, s_assd = take(k), take(k), take(k)
-    out = {"n_items": n_items, "confusion": cm, "contour_items": nvalid}
+    n_over, n_bad = (int(round(x)) for x in take(2))
+    out = {"n_items": n_items, "confusion": cm, "contour_items": nvalid, "n_overflow_items": n_over,
+           "n_bad_label_items": n_bad}
     out.update(derive.count_metrics(*derive.class_counts(cm)))          # pooled (micro) ratios per class
     denom = max(n_items, 1) * width
     out["thickness_difference"] = thick.astype(np.float64) / denom       # mean over all columns of all items
@@ -92,56 +107,64 @@ def all_reduce_sum(vec, world, device=None, group=None):
 
 
 def base_len(num_classes):
+    """Length of the SUM-reducible head of the totals vector (``octm_totals_sum_len``)."""
     k = num_classes
-    return 1 + k * k + k + 2 * (k - 1) + 4 * k
+    return 1 + k * k + k + 2 * (k - 1) + 4 * k + 2
+
+
+def _enqueue_reduce(res, world, group, want_max):
+    """(local, reduced) vectors: ``reduced`` = totals summed (head) / maximised (Hausdorff maxima) over the
+    ranks, enqueued on the current stream for CUDA totals.  No host round trip."""
+    k = res.labels.num_classes
+    nb = base_len(k)
+    local = res.totals
+    reduced = local.clone()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(reduced[:nb], op=dist.ReduceOp.SUM, group=group)
+        if want_max:
+            dist.all_reduce(reduced[nb:nb + k], op=dist.ReduceOp.MAX, group=group)
+    return local, reduced
+
+
+def _finish(res, world, group, want_max, local, reduced):
+    """Read the reduced totals back (one small D2H) and take the decisions EVERY rank must take alike, from the
+    REDUCED vector: ``n_bad_label_items > 0`` raises ValueError on all ranks; ``n_overflow_items > 0`` (a contour
+    longer than max_pts on ANY rank) makes every rank settle its own overflowed items and join a second
+    reduction.  Deciding from the local flags would leave the other ranks outside the second collective."""
+    import torch
+    k, w = res.labels.num_classes, res.labels.width
+    nb = base_len(k)
+    for attempt in range(2):
+        both = torch.stack([local, reduced]).cpu().numpy()              # one D2H
+        vec_local, vec = both[0], both[1]
+        if int(round(vec[nb - 1])) > 0 and res.validate:
+            res._totals_host, res._final, res._inputs = vec_local, True, None
+            raise ValueError(f"{int(round(vec[nb - 1]))} item(s) hold a label >= num_classes {k}")
+        if int(round(vec[nb - 2])) > 0 and attempt == 0 and res.contours is not None:
+            res.settle_overflow(vec_local)                               # local redo (no-op on ranks without overflow)
+            local, reduced = _enqueue_reduce(res, world, group, want_max)
+            continue
+        break
+    if res._totals_host is None:
+        res._totals_host, res._final, res._inputs = vec_local, True, None
+    _check_exact(vec_local, k)
+    out = unpack(vec[:nb], k, w)
+    if want_max:
+        out["hausdorff_distance_max"] = np.where(vec[nb:nb + k] < 0, np.nan, vec[nb:nb + k])
+    return out
 
 
 def dataset_totals(res, world, device=None, group=None, want_max=False):
     """Dataset-level numbers over all ranks' shards from one SuiteResult per rank.
 
-    The per-rank partial sums come from the device-side totals kernel.  With world > 1 they are
-    summed across ranks by ONE float64 all-reduce issued directly on the device vector (stream
-    ordered after the kernels, no host round trip before the collective); a single small D2H then
-    brings the reduced sums, this rank's maxima and its overflow flags to the host."""
-    k, w = res.labels.num_classes, res.labels.width
-    nb = base_len(k)
-    if world > 1 and res.totals is not None and res.totals.is_cuda and not res._final and res._totals_host is None:
-        import torch.distributed as dist
-        local = res.totals
-        reduced = local.clone()
-        dist.all_reduce(reduced[:nb], op=dist.ReduceOp.SUM, group=group)
-        if want_max:
-            dist.all_reduce(reduced[nb:nb + k], op=dist.ReduceOp.MAX, group=group)
-        both = __import__("torch").stack([local, reduced]).cpu().numpy()      # one D2H
-        res._totals_host = None
-        vec_local, vec = both[0], both[1]
-        if int(vec_local[-1]) & 12 and res.contours is not None:             # a contour overflowed on this rank:
-            res.totals_host()                                                 # redo it, then reduce again (rare)
-            return dataset_totals(res, world, device, group, want_max)
-        res._totals_host, res._final, res._inputs = vec_local, True, None
-        if np.any(np.abs(vec_local[:nb - 3 * k]) >= _EXACT_LIMIT):
-            raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")
-        out = unpack(vec[:nb], k, w)
-        if want_max:
-            out["hausdorff_distance_max"] = np.where(vec[nb:nb + k] < 0, np.nan, vec[nb:nb + k])
-        return out
-    vec = res.totals_host()
-    base = vec[:nb].copy()
-    if np.any(np.abs(base[:nb - 3 * k]) >= _EXACT_LIMIT):
-        raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")
-    if device is None and world > 1:
-        device = res.labels.counts.device
-    out = unpack(all_reduce_sum(base, world, device, group), k, w)
-    if want_max:
-        local = vec[nb:nb + k].copy()
-        if world > 1:
-            import torch
-            import torch.distributed as dist
-            t = torch.from_numpy(local).to(device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            local = t.cpu().numpy()
-        out["hausdorff_distance_max"] = np.where(local < 0, np.nan, local)
-    return out
+    The per-rank partial sums come from the device-side totals kernel and are summed across ranks by ONE
+    float64 all-reduce issued directly on the device vector (stream ordered after the kernels, no host round
+    trip before the collective); a single small D2H then brings the reduced sums and this rank's own vector
+    to the host.  Contour-overflow retries and the invalid-label error are decided from the reduced vector,
+    i.e. collectively (see ``_finish``)."""
+    local, reduced = _enqueue_reduce(res, world, group, want_max)
+    return _finish(res, world, group, want_max, local, reduced)
 
 
 class PendingTotals:
@@ -152,42 +175,15 @@ class PendingTotals:
         self.local, self.reduced = local, reduced
 
     def result(self):
-        """One small D2H; redoes (and re-reduces) the rare items whose contour overflowed."""
-        res, k, w = self.res, self.res.labels.num_classes, self.res.labels.width
-        nb = base_len(k)
-        if self.reduced is None:
-            return dataset_totals(res, self.world, group=self.group, want_max=self.want_max)
-        import torch
-        both = torch.stack([self.local, self.reduced]).cpu().numpy()
-        vec_local, vec = both[0], both[1]
-        if int(vec_local[-1]) & 12 and res.contours is not None and not res._final:
-            res.totals_host()
-            return dataset_totals(res, self.world, group=self.group, want_max=self.want_max)
-        if res._totals_host is None:
-            res._totals_host, res._final, res._inputs = vec_local, True, None
-        if np.any(np.abs(vec_local[:nb - 3 * k]) >= _EXACT_LIMIT):
-            raise OverflowError("an integer partial exceeds 2**53 and would not be exact in the float64 all-reduce")
-        out = unpack(vec[:nb], k, w)
-        if self.want_max:
-            out["hausdorff_distance_max"] = np.where(vec[nb:nb + k] < 0, np.nan, vec[nb:nb + k])
-        return out
+        """One small D2H; overflow retries are collective (every rank re-reduces when any rank overflowed)."""
+        return _finish(self.res, self.world, self.group, self.want_max, self.local, self.reduced)
 
 
 def dataset_totals_async(res, world, group=None, want_max=False):
     """Enqueue the cross-rank reduction of ``res.totals`` on the current stream and return a
     ``PendingTotals``; nothing is copied to the host until ``.result()``.  Lets a caller keep several
     evaluations in flight (the benchmark's device-timed region does)."""
-    if res.totals is None or not res.totals.is_cuda:
-        return PendingTotals(res, world, group, want_max, None, None)
-    k = res.labels.num_classes
-    nb = base_len(k)
-    local = res.totals
-    reduced = local.clone()
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(reduced[:nb], op=dist.ReduceOp.SUM, group=group)
-        if want_max:
-            dist.all_reduce(reduced[nb:nb + k], op=dist.ReduceOp.MAX, group=group)
+    local, reduced = _enqueue_reduce(res, world, group, want_max)
     return PendingTotals(res, world, group, want_max, local, reduced)
 
 

@@ -218,7 +218,7 @@ class ContourOut:
     max_pts: int = 0
 
 
-_SCRATCH = {}      # device -> grow-only int32 scratch for contour vertices (pure workspace, never returned)
+_SCRATCH = {}      # (device, stream) -> grow-only int32 scratch for contour vertices (pure workspace, never returned)
 
 
 _STAGING = {}      # device -> (copy stream, grow-only uint8 staging buffer of evaluate_host)
@@ -237,12 +237,15 @@ def _staging(dev, nbytes):
 
 
 def _vertex_scratch(dev, numel):
-    buf = _SCRATCH.get(dev)
+    """Grow-only int32 workspace, one per (device, stream): every consumer of a buffer is enqueued on the stream it
+    is keyed by, so reuse is stream-ordered and two streams never share scratch."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _SCRATCH.get(key)
     if buf is None or buf.numel() < numel:
-        _SCRATCH.pop(dev, None)
+        _SCRATCH.pop(key, None)
         buf = None
         buf = torch.empty((numel,), dtype=torch.int32, device=dev)
-        _SCRATCH[dev] = buf
+        _SCRATCH[key] = buf
     return buf[:numel]
 
 
@@ -314,21 +317,32 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
 
 
 def _retry_overflow(out, yt, yp, k, first_pos, keep=False):
-    """Re-run, with the largest vertex bound, the (rare) items whose contour overflowed ``max_pts``.
-    Returns True when something was redone.  Costs one device->host sync."""
-    over = ((out.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0).any(dim=1)
+    """Re-run, with a larger vertex bound, the (rare) items whose contour overflowed ``max_pts``.  The bound
+    escalates geometrically (x8 per round, up to MAX_MAX_PTS) and every round is chunked so that its vertex and
+    distance scratch stays below CONTOUR_CHUNK_BYTES, like the first pass.  Returns True when something was
+    redone.  Costs one device->host sync per round."""
+    over_bits = _lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW
+    over = ((out.flags & over_bits) != 0).any(dim=1)
     if not bool(over.any()):
         return False
     if keep:
         raise _lib.OctmError(f"a contour has more than max_pts={out.max_pts} vertices; raise max_pts")
     idx = torch.nonzero(over).flatten()
-    big = MAX_MAX_PTS
-    redo = _contour_chunk(yt[idx].contiguous(), yp[idx].contiguous(), k, first_pos[idx].contiguous(), big, False, False)
-    still = (redo.flags & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW)) != 0
-    if bool(still.any()):
-        raise _lib.OctmError(f"a contour has more than {big} vertices: pass a larger max_pts")
-    for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist"):
-        getattr(out, f)[idx] = getattr(redo, f)
+    big = max(int(out.max_pts), 8)
+    while idx.numel():
+        if big >= MAX_MAX_PTS:
+            raise _lib.OctmError(f"a contour has more than {MAX_MAX_PTS} vertices: pass a larger max_pts")
+        big = min(big * 8, MAX_MAX_PTS)
+        per_item = k * 2 * big * 4 * 2
+        chunk = max(1, CONTOUR_CHUNK_BYTES // per_item)
+        still = []
+        for s0 in range(0, idx.numel(), chunk):
+            sub = idx[s0:s0 + chunk]
+            redo = _contour_chunk(yt[sub].contiguous(), yp[sub].contiguous(), k, first_pos[sub].contiguous(), big, False, False)
+            for f in ("n_pts", "flags", "max_sq", "p95_sq", "sum_dist"):
+                getattr(out, f)[sub] = getattr(redo, f)
+            still.append(sub[((redo.flags & over_bits) != 0).any(dim=1)])
+        idx = torch.cat(still)
     return True
 
 
@@ -360,23 +374,38 @@ class SuiteResult:
     boundary_metrics: torch.Tensor | None = None
     totals: torch.Tensor | None = None
     _inputs: tuple | None = field(default=None, repr=False)
+    validate: bool = True
     _final: bool = field(default=False, repr=False)
     _host: dict | None = field(default=None, repr=False)
     _totals_host: np.ndarray | None = field(default=None, repr=False)
 
+    def settle_overflow(self, vec):
+        """Redo (with a larger vertex bound) this batch's items whose contour overflowed ``max_pts`` and
+        recompute the epilogue; ``vec`` is the host copy of ``totals``.  No-op when nothing overflowed here.
+        Returns True when something was redone."""
+        if self.contours is None or self._final:
+            return False
+        self._final = True
+        if not int(vec[-1]) & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW):
+            return False
+        yt, yp = self._inputs
+        _retry_overflow(self.contours, yt, yp, self.labels.num_classes, self.labels.first_pos)
+        self.class_metrics, self.boundary_metrics, self.totals = derive_on_device(self.labels, self.contours, self.num_items)
+        return True
+
     def totals_host(self):
-        """The totals vector on the host (one small D2H).  Also where contour overflow is noticed: the
-        vector's last entry ORs all contour flags, and overflowing items are redone before returning."""
+        """The totals vector on the host (one small D2H).  Also where the two deferred checks happen: items with
+        a label >= num_classes raise ValueError (``validate=True``), and items whose contour overflowed
+        ``max_pts`` are redone before returning."""
         if self._totals_host is None:
             vec = self.totals.cpu().numpy()
-            if self.contours is not None and not self._final:
-                self._final = True
-                if int(vec[-1]) & (_lib.CF_TRUE_OVERFLOW | _lib.CF_PRED_OVERFLOW):
-                    yt, yp = self._inputs
-                    _retry_overflow(self.contours, yt, yp, self.labels.num_classes, self.labels.first_pos)
-                    self.class_metrics, self.boundary_metrics, self.totals = derive_on_device(
-                        self.labels, self.contours, self.num_items)
-                    vec = self.totals.cpu().numpy()
+            nb = int(_lib.load().octm_totals_sum_len(self.labels.num_classes))
+            if self.validate and int(round(vec[nb - 1])) > 0:
+                self._inputs = None
+                raise ValueError(f"{int(round(vec[nb - 1]))} item(s) hold a label >= num_classes "
+                                 f"{self.labels.num_classes}")
+            if self.settle_overflow(vec):
+                vec = self.totals.cpu().numpy()
             self._inputs = None
             self._totals_host = vec
         return self._totals_host
@@ -441,12 +470,16 @@ class SuiteResult:
         return m
 
 
-def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS, timers=None):
+def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS, timers=None,
+             validate=True):
     """The full suite on a batch of label maps: fused label pass, contour kernels, float64 epilogue.
 
     Everything is launched asynchronously on the current stream; nothing is read back until
     ``totals_host()`` / ``metrics()`` / ``integers()`` is called on the result.
-    ``timers``: optional dict filled with (start, end) CUDA-event pairs per kernel family."""
+    ``timers``: optional dict filled with (start, end) CUDA-event pairs per kernel family.
+    ``validate``: a label >= num_classes (an ignore label such as 255, a wrong class count) raises ValueError when
+    the results are read.  The check costs nothing extra: the label pass never aliases such a pixel into another
+    class but drops it, so the item's confusion counts do not add up to H * W, which the totals kernel counts."""
     yt, yp = _check_pair(y_true, y_pred)
     # the contour stage uses the label pass's boundary rows to skip the walk on layered maps
     lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries or contours,
@@ -458,7 +491,7 @@ def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, ma
         if not boundaries:
             lp.bnd_true = lp.bnd_pred = None
     cls, bnd, tot = derive_on_device(lp, ct, yt.shape[0], timers)
-    return SuiteResult(yt.shape[0], lp, ct, cls, bnd, tot, (yt, yp) if contours else None)
+    return SuiteResult(yt.shape[0], lp, ct, cls, bnd, tot, (yt, yp) if contours else None, validate=bool(validate))
 
 
 def _cat_results(parts):
@@ -478,7 +511,7 @@ def _cat_results(parts):
                         cts[0].max_pts)
     n = sum(p.num_items for p in parts)
     cls, bnd, tot = derive_on_device(lp, ct, n)            # per-item values again + totals of the whole batch
-    res = SuiteResult(n, lp, ct, cls, bnd, tot)
+    res = SuiteResult(n, lp, ct, cls, bnd, tot, validate=parts[0].validate)
     res._final = True
     return res
 
@@ -496,7 +529,7 @@ def _pinned(nbytes):
 
 
 def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, chunk_items=None,
-                  max_pts=DEFAULT_MAX_PTS, pack=False, pack_threads=0):
+                  max_pts=DEFAULT_MAX_PTS, pack=False, pack_threads=0, validate=True):
     """The full suite on HOST label maps (numpy arrays or CPU torch tensors, ideally pinned).
 
     Items are streamed to the GPU in chunks through two staging buffers: the host->device copy of
@@ -593,7 +626,8 @@ def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, ch
             compute.wait_event(ready.pop(ci))
             if use_pack:
                 expand(ci)
-            parts.append(evaluate(bt[:e0 - s0], bp[:e0 - s0], num_classes, contours=contours, max_pts=max_pts))
+            parts.append(evaluate(bt[:e0 - s0], bp[:e0 - s0], num_classes, contours=contours, max_pts=max_pts,
+                                  validate=validate))
             done = torch.cuda.Event()
             done.record(compute)
             freed[ci & 1] = done
