@@ -58,6 +58,14 @@ OCTM_API const char* octm_last_error(void);
 /* Number of launches of this library's kernels since load (all entry points, this process). */
 OCTM_API uint64_t octm_launch_count(void);
 
+/* Per-kernel device timing for benchmarks.  octm_profile_enable(1) clears earlier records and makes every kernel
+ * launch of the library record two CUDA events on its launch stream; octm_profile_enable(0) stops and clears.
+ * octm_profile_report synchronises with the recorded launches and writes one line per kernel,
+ * "<kernel> <launches> <total ms>\n", in first-launch order, NUL-terminated and truncated to cap bytes;
+ * it returns the size the full report needs.  Off by default; not meant for timed regions. */
+OCTM_API int octm_profile_enable(int on);
+OCTM_API size_t octm_profile_report(char* buf, size_t cap);
+
 /* ---------------------------------------------------------------------------------------------
  * K1  confusion matrix.  counts[i][t][p] = #{pixels of item i with y_true == t and y_pred == p}.
  * One K x K uint64 matrix per item replaces the reference's per-class recomputation of
@@ -153,6 +161,18 @@ OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int
                       int max_pts, uint32_t* n_pts, uint32_t* flags, uint32_t* max_sq,
                       uint32_t* p95_sq, double* sum_dist, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* The same metrics for callers that ran octm_label_pass_u8 first (the batched suite does): first_pos AND the boundary
+ * rows bnd_true / bnd_pred [n][K-1][W] (may both be NULL) are handed in.  Pairs whose two contours are height
+ * functions over the columns -- verified against the label maps, the case of layered retinas -- are measured
+ * straight from the boundary rows in shared memory: their vertex lists never reach HBM.  Everything else (blobs,
+ * broken or touching layers, stray pixels above a layer) goes through the vertex lists like octm_contour2d_u8.
+ * Identical outputs either way.  workspace: 2 * round_up(n * K * 2 * max_pts * 4, 256) bytes (vertices + d2). */
+OCTM_API int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                              int num_classes, const uint32_t* first_pos, const int32_t* bnd_true,
+                              const int32_t* bnd_pred, int max_pts, uint32_t* n_pts, uint32_t* flags,
+                              uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* The two stages of the above, exposed for tests and for callers that want the vertices.
  *   verts   uint32 [n][K][2][max_pts]  packed (y2 << 16 | x2) doubled-lattice vertices of contour [0]: the

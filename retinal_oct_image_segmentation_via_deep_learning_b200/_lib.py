@@ -32,6 +32,8 @@ SIGNATURES = {
     "octm_abi_version": (_INT, []),
     "octm_last_error": (_c.c_char_p, []),
     "octm_launch_count": (_c.c_uint64, []),
+    "octm_profile_enable": (_INT, [_INT]),
+    "octm_profile_report": (_c.c_size_t, [_c.c_char_p, _c.c_size_t]),
     "octm_confusion_u8": (_INT, [_P, _P, _I64, _I64, _INT, _P, _P]),
     "octm_column_scan_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P]),
     "octm_boundary_error_i32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
@@ -40,6 +42,7 @@ SIGNATURES = {
     "octm_validate_labels_u8": (_INT, [_P, _I64, _P, _P]),
     "octm_contour2d_workspace_bytes": (_c.c_size_t, [_I64, _INT, _INT, _INT, _INT]),
     "octm_contour2d_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _INT, _P, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
+    "octm_contour2d_metrics_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
     "octm_first_pos_u8": (_INT, [_P, _I64, _I64, _INT, _P, _P]),
     "octm_contour2d_trace_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _INT, _P, _P, _P, _P]),
     "octm_contour2d_distance": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _INT, _P]),
@@ -97,3 +100,23 @@ def call(name, *args):
 
 def launch_count():
     return int(load().octm_launch_count())
+
+
+class kernel_profile:
+    """``with kernel_profile() as prof: ...`` -> ``prof.kernels`` = {kernel: (launches, total ms)} of every liboctm
+    kernel launched inside the block (CUDA events on the launch streams; for benchmarks, outside timed regions)."""
+
+    def __enter__(self):
+        load().octm_profile_enable(1)
+        self.kernels = {}
+        return self
+
+    def __exit__(self, *exc):
+        lib = load()
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.octm_profile_report(buf, len(buf))
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            self.kernels[name] = (int(n), float(ms))
+        lib.octm_profile_enable(0)
+        return False

@@ -116,13 +116,13 @@ static int launch_argmax(const void* scores, int64_t n_items, int K, int64_t P, 
         long long blocks = (n_items * (P / VPT) + 255) / 256;
         const long long cap = static_cast<long long>(sms) * 8;
         if (blocks > cap) blocks = cap;
-        argmax_planes_kernel<T, 4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(s, n_items, K, P, labels);
+        OCTM_TIMED("argmax_planes_kernel", st) argmax_planes_kernel<T, 4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(s, n_items, K, P, labels);
         return check_launch("argmax_planes_kernel");
     }
     long long blocks = (n_items * P + 255) / 256;
     const long long cap = static_cast<long long>(sms) * 16;
     if (blocks > cap) blocks = cap;
-    argmax_generic_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, st>>>(s, n_items, K, P, channels_last ? 1 : P,
+    OCTM_TIMED("argmax_generic_kernel", st) argmax_generic_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, st>>>(s, n_items, K, P, channels_last ? 1 : P,
                                                                            channels_last ? K : 1, labels);
     return check_launch("argmax_generic_kernel");
 }

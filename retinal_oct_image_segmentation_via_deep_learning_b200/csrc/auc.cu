@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kAucThreads, 1) auc_kernel(const AucParams prm
 
 template <class ScoreT, class KeyT>
 static int launch_auc(AucParams p, int ctas, cudaStream_t st) {
-    auc_kernel<ScoreT, KeyT><<<ctas, kAucThreads, 0, st>>>(p);
+    OCTM_TIMED("auc_kernel", st) auc_kernel<ScoreT, KeyT><<<ctas, kAucThreads, 0, st>>>(p);
     return check_launch("auc_kernel");
 }
 

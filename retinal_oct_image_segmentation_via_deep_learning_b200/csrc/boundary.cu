@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kRowThreads) topology_kernel(const T* __restri
 template <class T>
 static int launch_boundary_float(const void* a, const void* b, long long rows, long long W, double* sq, double* ab, cudaStream_t st) {
     long long grid = rows < 148ll * 16 ? rows : 148ll * 16;
-    boundary_error_float_kernel<T><<<static_cast<unsigned>(grid), kRowThreads, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b),
+    OCTM_TIMED("boundary_error_float_kernel", st) boundary_error_float_kernel<T><<<static_cast<unsigned>(grid), kRowThreads, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b),
                                                                                       rows, W, sq, ab);
     return check_launch("boundary_error_float_kernel");
 }
@@ -101,7 +101,7 @@ template <class T>
 static int launch_topology(const void* pos, long long n, int Kb, long long W, double* sv, unsigned int* nv, cudaStream_t st) {
     const long long pairs = n * (Kb - 1);
     long long grid = pairs < 148ll * 16 ? pairs : 148ll * 16;
-    topology_kernel<T><<<static_cast<unsigned>(grid), kRowThreads, 0, st>>>(static_cast<const T*>(pos), n, Kb, W, sv, nv);
+    OCTM_TIMED("topology_kernel", st) topology_kernel<T><<<static_cast<unsigned>(grid), kRowThreads, 0, st>>>(static_cast<const T*>(pos), n, Kb, W, sv, nv);
     return check_launch("topology_kernel");
 }
 

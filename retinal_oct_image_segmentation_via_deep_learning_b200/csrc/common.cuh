@@ -34,6 +34,31 @@ inline int check_launch(const char* what) {
     return OCTM_OK;
 }
 
+// ---------------------------------------------------------------- per-kernel device timing (octm_profile_*)
+// Off by default: a launch site costs one relaxed atomic load.  When enabled, every kernel launch of the
+// library is bracketed by two CUDA events on ITS launch stream; octm_profile_report() turns them into
+// per-kernel totals.  Used by bench.py on separate, untimed steps (never inside a timed region).
+extern std::atomic<int> g_profile;
+struct ProfScope {
+    int slot;
+    bool first;
+    cudaStream_t stream;
+    ProfScope(const char* name, cudaStream_t s) : slot(-1), first(true), stream(s) {
+        if (g_profile.load(std::memory_order_relaxed)) begin(name);
+    }
+    ~ProfScope() {
+        if (slot >= 0) end();
+    }
+    bool once() {
+        const bool f = first;
+        first = false;
+        return f;
+    }
+    void begin(const char* name);
+    void end();
+};
+#define OCTM_TIMED(name, stream) for (octm::ProfScope octm_ps_(name, stream); octm_ps_.once();)
+
 int sm_count();            // SMs of the current device (cached per device)
 int max_optin_smem();      // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device
 

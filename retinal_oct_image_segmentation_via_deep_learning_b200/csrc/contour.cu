@@ -45,6 +45,8 @@ struct TraceParams {
 };
 
 constexpr uint32_t kTraceTodo = 0xffffffffu;
+constexpr uint32_t kLayeredBit = 0x80000000u;    // n_pts: contour verified as a height function, vertices not emitted
+constexpr uint32_t kNeedsSearch = 0xfffffffeu;   // max_sq: unit left to the general (vertex-list) distance search
 
 // Both row caches of the walk in one go: 16 aligned label bytes for the even-row cache and 16 for the odd-row
 // cache, each loaded only when its predicate is set (lanes of a warp hit and miss independently: predicated
@@ -215,6 +217,10 @@ __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const Trace
 #ifndef OCTM_LAYERED_MINB
 #define OCTM_LAYERED_MINB 8
 #endif
+// EMIT = false: verification only.  A verified contour gets n_pts = (vertex count | kLayeredBit) and no vertices
+// are written: layered_distance_kernel works from the boundary rows and emits vertices only for the pairs it
+// cannot finish itself.
+template <bool EMIT>
 __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(const TraceParams prm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = prm.K, H = prm.H, W = prm.W;
@@ -306,6 +312,9 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
                 const uint32_t x2 = 2u * static_cast<uint32_t>(x);
                 const uint32_t ua = static_cast<uint32_t>(ha), ub = static_cast<uint32_t>(hb), uw = static_cast<uint32_t>(W);
                 minkey = min(minkey, min(ua * uw + static_cast<uint32_t>(x), ub * uw + static_cast<uint32_t>(x) + 1u));
+            }
+            if (EMIT && valid) {
+                const uint32_t x2 = 2u * static_cast<uint32_t>(x);
                 uint32_t* o = out + pos;
                 *o++ = (static_cast<uint32_t>(2 * ha - 1) << 16) | x2;
                 uint32_t va = (static_cast<uint32_t>(2 * min(ha, hb)) << 16) | (x2 + 1u);
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
             }
         }
         if (ok) ok = !__any_sync(0xffffffffu, bad) && __reduce_min_sync(0xffffffffu, minkey) == seed;
-        if (lane == 0) *np = ok ? base : kTraceTodo;
+        if (lane == 0) *np = ok ? (EMIT ? base : (base | kLayeredBit)) : kTraceTodo;
     }
 }
 
@@ -666,6 +675,7 @@ struct SearchParams {
     uint32_t* p95_sq;        // [n][K][2][2]
     double* sum_dist;        // [n][K][2]
     bool keep_d2;            // store every unit's squared distances as well
+    bool only_marked;        // search only the units whose max_sq is kNeedsSearch
 };
 
 constexpr int kCountBins = 1024;                    // squared distances 0, 2, .. 2046 are counted in shared memory
@@ -765,6 +775,7 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
         const long long pair = unit >> 1;
         const int dir = static_cast<int>(unit & 1);
         // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
+        if (prm.only_marked && prm.max_sq[unit] != kNeedsSearch) continue;      // CTA-uniform
         const int ns_all = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
         const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
         if (ns_all == 0 || nq == 0) {
@@ -924,6 +935,7 @@ struct ColumnParams {
     uint32_t* p95_sq;        // [n][K][2][2]
     double* sum_dist;        // [n][K][2]
     bool keep_d2;
+    bool only_marked;        // search only the units whose max_sq is kNeedsSearch (the rest is already finished)
 };
 
 // Query groups: kColGroup consecutive lanes share one column span (their sources are read from one address per
@@ -1070,6 +1082,7 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
         const long long pair = unit >> 1;
         const int dir = static_cast<int>(unit & 1);
         // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
+        if (prm.only_marked && prm.max_sq[unit] != kNeedsSearch) continue;      // CTA-uniform
         const int ns = static_cast<int>(min(prm.n_pts[pair * 2 + dir], static_cast<uint32_t>(cap)));
         const int nq = static_cast<int>(min(prm.n_pts[pair * 2 + 1 - dir], static_cast<uint32_t>(cap)));
         if (ns == 0 || nq == 0) {
@@ -1325,6 +1338,228 @@ __global__ void __launch_bounds__(128) distance_select_kernel(const SelectParams
 }
 
 
+// ------------------------------------------------------------------------------ layered pairs: fused distances
+// When BOTH contours of an (item, class) pair were verified as height functions (trace_layered_kernel<false>),
+// neither vertex list ever reaches HBM.  One WARP per pair keeps, for each map, two int16 tables over the doubled
+// lattice columns c in [0, 2 W - 1) in shared memory -- the contour's vertices of column c are the lattice rows
+// lo[c], lo[c] + 2, .., hi[c]:
+//     c = 2 x      one vertex          lo = hi = 2 h(x) - 1
+//     c = 2 x + 1  |h(x+1) - h(x)|     lo = 2 min(h(x), h(x+1)), hi = 2 max(..) - 2;  none: lo = 32767, hi = -32768
+// (built from the label pass's boundary rows: 4 KB per map for W = 512).  The squared distance from a query vertex
+// (qy, qx) to the vertices of source column c is  max(lo - qy, qy - hi, |c - qx| & 1)^2 + (c - qx)^2  (same column
+// parity = same row parity, so an in-range query hits a vertex exactly; the other parity misses by one row), i.e.
+// every source COLUMN costs a constant, whatever its vertex count.  A query scans the columns qx, qx -+ 1, qx -+ 2,
+// .. until d^2 can no longer beat its best: exact, and ~4 x (contour distance in pixels) columns per query.
+// Queries are the vertices of the other map's tables: the W even-column vertices straight from the lanes (lane =
+// column), the odd-column runs compacted through a per-warp ring so that every round works on 32 real queries.
+// The minima are counted like in the vertex-list search (count_minima / stats_from_counters).  Pairs this kernel
+// cannot finish -- a side that has to be walked, a distance the counters cannot hold -- get their verified sides'
+// vertices emitted from the tables (column order) and both units marked kNeedsSearch for distance_column_kernel.
+constexpr int kLdWarps = 4;           // one CTA = one (item, class) pair: the tables are shared, the query blocks dealt out
+constexpr int kLdPad = 32;            // empty columns on both sides of a table: the scan needs no clamping up to d = 32
+constexpr int kLdRing = 256;          // odd-column query ring per warp (entries)
+#ifndef OCTM_LD_MINB
+#define OCTM_LD_MINB 10
+#endif
+
+struct LayeredDistParams {
+    const uint32_t* first_pos;   // [n][2][K]
+    const int* bnd_t;            // [n][K-1][W]
+    const int* bnd_p;
+    long long n_pairs;           // n * K
+    int W, K, max_pts;
+    int tab;                     // int16 entries per table: 2 W - 1 + 2 kLdPad, rounded up to a multiple of 8
+    uint32_t* verts;             // [n][K][2][max_pts]  written only for pairs left to the vertex-list search
+    uint32_t* n_pts;             // [n][K][2]  in: count | kLayeredBit, kTraceTodo or 0;  out: kLayeredBit cleared
+    uint32_t* max_sq;            // [n][K][2]
+    uint32_t* p95_sq;            // [n][K][2][2]
+    double* sum_dist;            // [n][K][2]
+};
+
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
+
+// nearest vertex of the tabulated contour (lo / hi point at column 0 of the tables) to the query (qy, qx)
+__device__ __forceinline__ int layered_nearest(const short* lo, const short* hi, int qy, int qx, int ncol) {
+    const short* l0 = lo + qx;
+    const short* h0 = hi + qx;
+    const int dy0 = max3i(l0[0] - qy, qy - h0[0], 0);
+    int best = dy0 * dy0;
+    int d = 1;
+    // columns qx -+ d, two distances per pass (odd d: the other row parity, a miss by at least one row)
+    while (d * d < best && d < kLdPad) {
+        const int a0 = max3i(l0[-d] - qy, qy - h0[-d], 1), a1 = max3i(l0[d] - qy, qy - h0[d], 1);
+        const int b0 = max3i(l0[-d - 1] - qy, qy - h0[-d - 1], 0), b1 = max3i(l0[d + 1] - qy, qy - h0[d + 1], 0);
+        const int d2 = d * d, e2 = (d + 1) * (d + 1);
+        best = min3i(best, a0 * a0 + d2, a1 * a1 + d2);
+        best = min3i(best, b0 * b0 + e2, b1 * b1 + e2);
+        d += 2;
+    }
+    // contours further apart than the pad (rare): the same scan with clamped columns (the pads are empty columns)
+    for (; d * d < best; ++d) {
+        const int cl = max(qx - d, -1), cr = min(qx + d, ncol);
+        const int par = d & 1;
+        const int a0 = max3i(lo[cl] - qy, qy - hi[cl], par), a1 = max3i(lo[cr] - qy, qy - hi[cr], par);
+        best = min3i(best, a0 * a0 + d * d, a1 * a1 + d * d);
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_kernel(const LayeredDistParams prm) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t s_vmax[2], s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = prm.W, K = prm.K, tab = prm.tab, ncol = 2 * W - 1;
+    short* const tabs = reinterpret_cast<short*>(dsm);                                   // [map][lo | hi][tab]
+    uint32_t* const bins2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(tab) * 8);   // [dir][kCountBins / 2]
+    uint32_t* const ring = bins2 + kCountBins + warp * kLdRing;                          // this warp's ring
+    for (int i = tid; i < kCountBins; i += kLdWarps * 32) bins2[i] = 0;
+    for (int i = tid; i < 2 * tab; i += kLdWarps * 32) {                                 // the pads never change
+        const int m = i >= tab ? 1 : 0, j = i - m * tab;
+        if (j < kLdPad || j >= kLdPad + ncol) {
+            tabs[(2 * m) * tab + j] = 32767;
+            tabs[(2 * m + 1) * tab + j] = -32768;
+        }
+    }
+    const int nblk = (W + 31) >> 5;
+
+    for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
+        __syncthreads();                     // the previous pair is finished with the tables, the counters and s_*
+        const long long item = pair / K;
+        const int cls = static_cast<int>(pair - item * K);
+        const uint32_t n0 = prm.n_pts[pair * 2], n1 = prm.n_pts[pair * 2 + 1];
+        const bool lay0 = n0 != kTraceTodo && (n0 & kLayeredBit), lay1 = n1 != kTraceTodo && (n1 & kLayeredBit);
+        const uint32_t cnt0 = n0 & ~kLayeredBit, cnt1 = n1 & ~kLayeredBit;
+        if (n0 == 0 || n1 == 0) {            // a mask without a contour: nothing to measure (reference: IndexError)
+            if (tid < 2) {
+                const uint32_t n = tid ? n1 : n0;
+                prm.n_pts[pair * 2 + tid] = n != kTraceTodo ? (n & ~kLayeredBit) : n;
+                prm.max_sq[pair * 2 + tid] = (n0 == kTraceTodo || n1 == kTraceTodo) ? kNeedsSearch : 0u;
+                prm.p95_sq[pair * 4 + tid * 2] = prm.p95_sq[pair * 4 + tid * 2 + 1] = 0;
+                prm.sum_dist[pair * 2 + tid] = 0.0;
+            }
+            continue;
+        }
+        if (tid < 2) s_vmax[tid] = 0;
+        if (tid == 2) s_bad = 0;
+        // ---- tables of the verified sides: warps 0-1 map 0, warps 2-3 map 1
+        {
+            const int m = warp >> 1;
+            if (m ? lay1 : lay0) {
+                const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
+                const uint32_t myfp = lane < K ? fp[lane] : OCTM_NO_SEED;
+                const int c00 = __ffs(__ballot_sync(0xffffffffu, myfp == 0u)) - 1;
+                const int brow = cls == c00 ? cls : cls - 1;                   // as in trace_layered_kernel
+                const int* hrow = (m ? prm.bnd_p : prm.bnd_t) + (item * (K - 1) + brow) * static_cast<long long>(W);
+                uint32_t* lo32 = reinterpret_cast<uint32_t*>(tabs + (2 * m) * tab + kLdPad);
+                uint32_t* hi32 = lo32 + (tab >> 1);
+                for (int x0 = (warp & 1) * 32; x0 < W; x0 += 64) {
+                    const int x = x0 + lane;
+                    const int h = hrow[min(x, W - 1)];
+                    int hn = __shfl_down_sync(0xffffffffu, h, 1);
+                    if (lane == 31) hn = hrow[min(x + 1, W - 1)];
+                    if (x < W) {             // columns 2 x and 2 x + 1 as one 32-bit store per table (column 2 W - 1 is a pad)
+                        const uint32_t e = static_cast<uint32_t>(2 * h - 1) & 0xffffu;
+                        const bool run = x + 1 < W && hn != h;
+                        const uint32_t ol = run ? static_cast<uint32_t>(2 * min(h, hn)) : 32767u;
+                        const uint32_t oh = run ? static_cast<uint32_t>(2 * max(h, hn) - 2) & 0xffffu : 0x8000u;
+                        lo32[x] = e | (ol << 16);
+                        hi32[x] = e | (oh << 16);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        bool done = lay0 && lay1;            // CTA-uniform
+        if (done) {
+            for (int dir = 0; dir < 2; ++dir) {
+                // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
+                const short* slo = tabs + (2 * dir) * tab + kLdPad;
+                const short* shi = slo + tab;
+                const short* qlo = tabs + (2 * (1 - dir)) * tab + kLdPad;
+                const short* qhi = qlo + tab;
+                uint32_t* bins = bins2 + dir * (kCountBins / 2);
+                uint32_t run_max = 0, head = 0, tail = 0;
+                bool run_bad = false;
+                for (int blk = warp; blk < nblk; blk += kLdWarps) {
+                    const int x = blk * 32 + lane;
+                    const bool valid = x < W;
+                    // the even-column vertex of column x
+                    const int best = valid ? layered_nearest(slo, shi, qlo[2 * x], 2 * x, ncol) : 0;
+                    count_minima(best, valid, lane, bins, run_max, run_bad);
+                    // the run between columns x and x + 1 joins the ring
+                    const bool hasrun = valid && x + 1 < W;
+                    const int rl = hasrun ? qlo[2 * x + 1] : 32767, rh = hasrun ? qhi[2 * x + 1] : -32768;
+                    const uint32_t len = rh >= rl ? static_cast<uint32_t>((rh - rl) >> 1) + 1u : 0u;
+                    uint32_t incl = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total > static_cast<uint32_t>(kLdRing - 32)) { run_bad = true; break; }   // absurdly steep: general path
+                    uint32_t at = tail + incl - len;
+                    for (uint32_t t = 0; t < len; ++t, ++at)
+                        ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(rl + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * x + 1);
+                    tail += total;
+                    __syncwarp();
+                    while (tail - head >= 32u) {
+                        const uint32_t q = ring[(head + lane) & (kLdRing - 1)];
+                        head += 32u;
+                        const int b = layered_nearest(slo, shi, static_cast<int>(q >> 16), static_cast<int>(q & 0xffffu), ncol);
+                        count_minima(b, true, lane, bins, run_max, run_bad);
+                    }
+                    __syncwarp();
+                }
+                if (tail != head) {
+                    const bool v = static_cast<uint32_t>(lane) < tail - head;
+                    const uint32_t q = ring[(head + (v ? lane : 0)) & (kLdRing - 1)];
+                    const int b = layered_nearest(slo, shi, static_cast<int>(q >> 16), static_cast<int>(q & 0xffffu), ncol);
+                    count_minima(b, v, lane, bins, run_max, run_bad);
+                }
+                publish_counts(run_max, run_bad, lane, &s_vmax[dir], &s_bad);
+            }
+            __syncthreads();                 // both directions counted
+            done = s_bad == 0;
+            if (done) {
+                if (warp < 2)
+                    stats_from_counters(bins2 + warp * (kCountBins / 2), s_vmax[warp], static_cast<int>(warp ? cnt0 : cnt1), lane,
+                                        prm.max_sq + pair * 2 + warp, prm.p95_sq + (pair * 2 + warp) * 2, prm.sum_dist + pair * 2 + warp);
+                if (tid >= 64 && tid < 66) prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
+                continue;
+            }
+            for (int i = tid; i < kCountBins; i += kLdWarps * 32) bins2[i] = 0;      // a value the counters cannot hold
+        }
+        // ---- left to the vertex-list search: emit the verified sides' vertices in column order (warp m: map m)
+        if (warp < 2 && (warp ? lay1 : lay0)) {
+            const int m = warp;
+            const short* lo = tabs + (2 * m) * tab + kLdPad;
+            const short* hi = lo + tab;
+            uint32_t* out = prm.verts + (pair * 2 + m) * static_cast<long long>(prm.max_pts);
+            uint32_t base = 0;
+            for (int c0 = 0; c0 < ncol; c0 += 32) {
+                const int c = c0 + lane;
+                const int l = c < ncol ? lo[c] : 32767, h = c < ncol ? hi[c] : -32768;
+                const uint32_t len = h >= l ? static_cast<uint32_t>((h - l) >> 1) + 1u : 0u;
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                uint32_t at = base + incl - len;
+                for (uint32_t t = 0; t < len; ++t, ++at)
+                    if (at < static_cast<uint32_t>(prm.max_pts))
+                        out[at] = (static_cast<uint32_t>(l + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(c);
+                base += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) prm.n_pts[pair * 2 + m] = m ? cnt1 : cnt0;
+        }
+        if (tid >= 64 && tid < 66) prm.max_sq[pair * 2 + (tid - 64)] = kNeedsSearch;
+    }
+}
+
 }  // namespace octm
 
 // ----------------------------------------------------------------------------------- C ABI
@@ -1346,9 +1581,50 @@ extern "C" int octm_first_pos_u8(const uint8_t* labels, int64_t n_items, int64_t
     if (n_items == 0) return OCTM_OK;
     if (!labels || !first_pos) return octm::fail(OCTM_ERR_INVALID, "null pointer");
     const long long grid = n_items < 148 * 8 ? n_items : 148 * 8;
-    octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    OCTM_TIMED("first_pos_kernel", static_cast<cudaStream_t>(stream)) octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         labels, n_items, item_elems, num_classes, first_pos, num_classes);
     return octm::check_launch("first_pos_kernel");
+}
+
+static bool layered_ok(const void* y_true, const void* y_pred, const void* bnd_true, const void* bnd_pred, int H, int W, int K) {
+    // layered fast path (needs the label pass's boundary rows): OCTM_TRACE_LAYERED=0 turns it off
+    static const bool env_layered = [] { const char* e = getenv("OCTM_TRACE_LAYERED"); return !(e && e[0] == '0'); }();
+    return env_layered && bnd_true != nullptr && bnd_pred != nullptr && H >= 2 && W % 2 == 0 && K >= 2 && K <= 32 &&
+           reinterpret_cast<uintptr_t>(y_true) % 2 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 2 == 0 &&
+           reinterpret_cast<uintptr_t>(bnd_true) % 8 == 0 && reinterpret_cast<uintptr_t>(bnd_pred) % 8 == 0;
+}
+
+template <bool EMIT>
+static int launch_layered_trace(const octm::TraceParams& p, cudaStream_t s) {
+    int fit = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_layered_kernel<EMIT>, 128, 0) != cudaSuccess || fit < 1) {
+        cudaGetLastError();
+        fit = 8;
+    }
+    long long grid = (p.n_items * p.K * 2 + 3) / 4;
+    const long long cap = static_cast<long long>(octm::sm_count()) * fit;
+    if (grid > cap) grid = cap;
+    OCTM_TIMED("trace_layered_kernel", s) octm::trace_layered_kernel<EMIT><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
+    return octm::check_launch("trace_layered_kernel");
+}
+
+static int launch_walk(const octm::TraceParams& p, cudaStream_t s) {
+    const bool words = p.W % 16 == 0 && reinterpret_cast<uintptr_t>(p.yt) % 16 == 0 && reinterpret_cast<uintptr_t>(p.yp) % 16 == 0;
+    const long long threads = p.n_items * p.K * 2;
+    static const int env_ctas = [] { const char* e = getenv("OCTM_TRACE_CTAS"); return e ? atoi(e) : 0; }();
+    int fit = 0;       // persistent grid: every CTA that can be resident (the walk is latency-bound: occupancy hides it)
+    if ((words ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<true>, 128, 0)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<false>, 128, 0)) != cudaSuccess || fit < 1) {
+        cudaGetLastError();
+        fit = 8;
+    }
+    const int ctas_per_sm = env_ctas > 0 ? env_ctas : fit;
+    long long grid = (threads + 127) / 128;
+    const long long cap = static_cast<long long>(octm::sm_count()) * ctas_per_sm;
+    if (grid > cap) grid = cap;
+    if (words) OCTM_TIMED("trace_kernel", s) octm::trace_kernel<true><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
+    else OCTM_TIMED("trace_kernel", s) octm::trace_kernel<false><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
+    return octm::check_launch("trace_kernel");
 }
 
 extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
@@ -1364,39 +1640,11 @@ extern "C" int octm_contour2d_trace_u8(const uint8_t* y_true, const uint8_t* y_p
         return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
     octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags,
                         bnd_true, bnd_pred, false};
-    const bool words = W % 16 == 0 && reinterpret_cast<uintptr_t>(y_true) % 16 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 16 == 0;
-    const long long threads = n_items * num_classes * 2;
-    // layered fast path (needs the label pass's boundary rows): OCTM_TRACE_LAYERED=0 turns it off
-    static const bool env_layered = [] { const char* e = getenv("OCTM_TRACE_LAYERED"); return !(e && e[0] == '0'); }();
-    if (env_layered && bnd_true != nullptr && H >= 2 && W % 2 == 0 && num_classes >= 2 && num_classes <= 32 &&
-        reinterpret_cast<uintptr_t>(y_true) % 2 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 2 == 0 &&
-        reinterpret_cast<uintptr_t>(bnd_true) % 8 == 0 && reinterpret_cast<uintptr_t>(bnd_pred) % 8 == 0) {
-        int fit = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_layered_kernel, 128, 0) != cudaSuccess || fit < 1) {
-            cudaGetLastError();
-            fit = 8;
-        }
-        long long grid = (threads + 3) / 4;
-        const long long cap = static_cast<long long>(octm::sm_count()) * fit;
-        if (grid > cap) grid = cap;
-        octm::trace_layered_kernel<<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
-        if (int e = octm::check_launch("trace_layered_kernel")) return e;
+    if (layered_ok(y_true, y_pred, bnd_true, bnd_pred, H, W, num_classes)) {
+        if (int e = launch_layered_trace<true>(p, s)) return e;
         p.only_todo = true;
     }
-    static const int env_ctas = [] { const char* e = getenv("OCTM_TRACE_CTAS"); return e ? atoi(e) : 0; }();
-    int fit = 0;       // persistent grid: every CTA that can be resident (the walk is latency-bound: occupancy hides it)
-    if ((W % 16 == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<true>, 128, 0)
-                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::trace_kernel<false>, 128, 0)) != cudaSuccess || fit < 1) {
-        cudaGetLastError();
-        fit = 8;
-    }
-    const int ctas_per_sm = env_ctas > 0 ? env_ctas : fit;
-    long long grid = (threads + 127) / 128;
-    const long long cap = static_cast<long long>(octm::sm_count()) * ctas_per_sm;
-    if (grid > cap) grid = cap;
-    if (words) octm::trace_kernel<true><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
-    else octm::trace_kernel<false><<<static_cast<unsigned>(grid), 128, 0, s>>>(p);
-    return octm::check_launch("trace_kernel");
+    return launch_walk(p, s);
 }
 
 static size_t dist_smem(int max_pts) {
@@ -1404,9 +1652,9 @@ static size_t dist_smem(int max_pts) {
     return static_cast<size_t>(max_pts) * 20 + 2 * (capb + caps) * 16;
 }
 
-extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
-                                       int max_pts, int H, int W, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
-                                       uint32_t* d2, int keep_d2, void* stream) {
+static int run_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes, int max_pts, int H,
+                        int W, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, uint32_t* d2, int keep_d2,
+                        bool only_marked, void* stream) {
     if (n_items < 0 || num_classes < 1 || max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "bad shape");
     if (H < 1 || W < 1 || H > 8192 || W > 8192) return octm::fail(OCTM_ERR_INVALID, "H, W outside [1, 8192]");
     if (n_items == 0) return OCTM_OK;
@@ -1422,6 +1670,7 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
         return 3;
     }();
     int mode = env_mode;
+    if (only_marked && mode != 3) mode = 0;         // the single-kernel check modes search every unit
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long n_pairs = n_items * num_classes;
     auto run_select = [&]() -> int {
@@ -1429,7 +1678,7 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
         long long kgrid = (n_pairs * 2 + 3) / 4;
         const long long kcap = static_cast<long long>(octm::sm_count()) * 16;
         if (kgrid > kcap) kgrid = kcap;
-        octm::distance_select_kernel<<<static_cast<unsigned>(kgrid), 128, 0, st>>>(kp);
+        OCTM_TIMED("distance_select_kernel", st) octm::distance_select_kernel<<<static_cast<unsigned>(kgrid), 128, 0, st>>>(kp);
         return octm::check_launch("distance_select_kernel");
     };
     if (mode == 3) {
@@ -1442,11 +1691,11 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
             if (cudaFuncSetAttribute(octm::distance_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)) != cudaSuccess)
                 return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_column_kernel) failed");
-            octm::ColumnParams cp{verts, n_pts, n_pairs * 2, max_pts, ncol, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0};
+            octm::ColumnParams cp{verts, n_pts, n_pairs * 2, max_pts, ncol, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0, only_marked};
             long long grid = n_pairs * 2;
             const long long cap = static_cast<long long>(octm::sm_count()) * 32;
             if (grid > cap) grid = cap;
-            octm::distance_column_kernel<<<static_cast<unsigned>(grid), octm::kColThreads, smem, st>>>(cp);
+            OCTM_TIMED("distance_column_kernel", st) octm::distance_column_kernel<<<static_cast<unsigned>(grid), octm::kColThreads, smem, st>>>(cp);
             if (int e = octm::check_launch("distance_column_kernel")) return e;
             return run_select();
         }
@@ -1462,11 +1711,11 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
         if (cudaFuncSetAttribute(octm::distance_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_search_kernel) failed");
-        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0};
+        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0, only_marked};
         long long grid = n_pairs * 2;
         const long long cap = static_cast<long long>(octm::sm_count()) * 32;
         if (grid > cap) grid = cap;
-        octm::distance_search_kernel<<<static_cast<unsigned>(grid), octm::kSearchThreads, smem, st>>>(sp);
+        OCTM_TIMED("distance_search_kernel", st) octm::distance_search_kernel<<<static_cast<unsigned>(grid), octm::kSearchThreads, smem, st>>>(sp);
         if (int e = octm::check_launch("distance_search_kernel")) return e;
         return run_select();
     }
@@ -1480,8 +1729,70 @@ extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_
     auto kern = mode == 2 ? octm::distance_kernel<false> : octm::distance_kernel<true>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, octm::max_optin_smem() - 4096) != cudaSuccess)
         return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_kernel) failed");
-    kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, st>>>(p);
+    OCTM_TIMED("distance_kernel", st) kern<<<static_cast<unsigned>(grid), octm::kDistThreads, smem, st>>>(p);
     return octm::check_launch("distance_kernel");
+}
+
+extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
+                                       int max_pts, int H, int W, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
+                                       uint32_t* d2, int keep_d2, void* stream) {
+    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, keep_d2, false, stream);
+}
+
+extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                                         int num_classes, const uint32_t* first_pos, const int32_t* bnd_true,
+                                         const int32_t* bnd_pred, int max_pts, uint32_t* n_pts, uint32_t* flags,
+                                         uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    if (int e = check_shape(n_items, H, W, num_classes, max_pts)) return e;
+    if (n_items == 0) return OCTM_OK;
+    if (!y_true || !y_pred || !first_pos || !n_pts || !flags || !max_sq || !p95_sq || !sum_dist)
+        return octm::fail(OCTM_ERR_INVALID, "null pointer");
+    if ((bnd_true == nullptr) != (bnd_pred == nullptr)) return octm::fail(OCTM_ERR_INVALID, "bnd_true/bnd_pred: both or neither");
+    const size_t verts_b = (static_cast<size_t>(n_items) * num_classes * 2 * max_pts * sizeof(uint32_t) + 255) & ~static_cast<size_t>(255);
+    if (workspace == nullptr || workspace_bytes < 2 * verts_b)
+        return octm::fail(OCTM_ERR_WORKSPACE, "workspace too small: need %zu B", 2 * verts_b);
+    uint32_t* verts = static_cast<uint32_t*>(workspace);
+    uint32_t* d2 = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + verts_b);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // OCTM_LAYERED_FUSED=0: always go through vertex lists (the round-1 path; tests compare the two)
+    static const bool env_fused = [] { const char* e = getenv("OCTM_LAYERED_FUSED"); return !(e && e[0] == '0'); }();
+    const int tab = (2 * W - 1 + 2 * octm::kLdPad + 7) & ~7;
+    const size_t smem = static_cast<size_t>(tab) * 8 + octm::kCountBins * 4 + octm::kLdWarps * octm::kLdRing * 4;
+    const bool fused = env_fused && layered_ok(y_true, y_pred, bnd_true, bnd_pred, H, W, num_classes) && H <= 4095 &&
+                       max_pts <= 0xffff && smem <= static_cast<size_t>(octm::max_optin_smem());
+    if (!fused) {
+        if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, bnd_true, bnd_pred, max_pts,
+                                            verts, n_pts, flags, stream))
+            return e;
+        return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, false, stream);
+    }
+    if (cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n_items * num_classes, s) != cudaSuccess)
+        return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
+    octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags,
+                        bnd_true, bnd_pred, false};
+    if (int e = launch_layered_trace<false>(p, s)) return e;               // verify only: n_pts = count | kLayeredBit
+    {
+        if (cudaFuncSetAttribute(octm::layered_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)) != cudaSuccess)
+            return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(layered_distance_kernel) failed");
+        int fit = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::layered_distance_kernel, octm::kLdWarps * 32, smem) != cudaSuccess || fit < 1) {
+            cudaGetLastError();
+            fit = 1;
+        }
+        const long long n_pairs = n_items * num_classes;
+        long long grid = n_pairs;
+        const long long cap = static_cast<long long>(octm::sm_count()) * fit;
+        if (grid > cap) grid = cap;
+        octm::LayeredDistParams lp{first_pos, bnd_true, bnd_pred, n_pairs, W, num_classes, max_pts, tab, verts, n_pts,
+                                   max_sq, p95_sq, sum_dist};
+        OCTM_TIMED("layered_distance_kernel", s) octm::layered_distance_kernel<<<static_cast<unsigned>(grid), octm::kLdWarps * 32, smem, s>>>(lp);
+        if (int e = octm::check_launch("layered_distance_kernel")) return e;
+    }
+    p.only_todo = true;
+    if (int e = launch_walk(p, s)) return e;                                // the contours the verification rejected
+    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, true, stream);
 }
 
 extern "C" size_t octm_contour2d_workspace_bytes(int64_t n_items, int H, int W, int num_classes, int max_pts) {
@@ -1510,10 +1821,10 @@ extern "C" int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
         // no label pass ran: find the first occurrences of both maps here, interleaved [n][2][K]
         const long long grid = n_items < 148 * 8 ? n_items : 148 * 8;
         cudaStream_t s = static_cast<cudaStream_t>(stream);
-        octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(y_true, n_items, static_cast<long long>(H) * W,
+        OCTM_TIMED("first_pos_kernel", s) octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(y_true, n_items, static_cast<long long>(H) * W,
                                                                          num_classes, fp_ws, 2 * num_classes);
         if (int e = octm::check_launch("first_pos_kernel")) return e;
-        octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(y_pred, n_items, static_cast<long long>(H) * W,
+        OCTM_TIMED("first_pos_kernel", s) octm::first_pos_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(y_pred, n_items, static_cast<long long>(H) * W,
                                                                          num_classes, fp_ws + num_classes, 2 * num_classes);
         if (int e = octm::check_launch("first_pos_kernel")) return e;
         first_pos = fp_ws;

@@ -29,6 +29,7 @@ struct DeriveParams {
     int H, W, K;
     double* cls;                        // [n][K][OCTM_NUM_CLASS_METRICS]
     double* bnd;                        // [n][K-1][3] or null
+    double* n_bad;                      // totals slot "n_bad_label_items" (zeroed before the launch) or null
 };
 
 __device__ __forceinline__ double percentile95(uint32_t lo_sq, uint32_t hi_sq, uint32_t m) {
@@ -55,6 +56,8 @@ __global__ void __launch_bounds__(128) derive_kernel(const DeriveParams p) {
             if (t == c) row += v;
             if (q == c) colsum += v;
         }
+    // the label pass drops pixels whose label is >= K: such an item's counts do not add up to H * W
+    if (c == 0 && p.n_bad != nullptr && total != static_cast<long long>(p.H) * p.W) atomicAdd(p.n_bad, 1.0);
     const long long tp = static_cast<long long>(cm[c * K + c]);
     const long long fn = row - tp, fp = colsum - tp, tn = total - tp - fn - fp;
     const long long st = tp + fn, sp = tp + fp;
@@ -115,7 +118,6 @@ struct TotalsParams {
     const double* cls;         // [n][K][OCTM_NUM_CLASS_METRICS]
     const uint32_t* flags;     // [n][K] or null
     long long n_items;
-    long long item_px;         // H * W
     int K;
     double* out;
 };
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(256) totals_kernel(const TotalsParams p) {
         if (tid == 0) p.out[0] = static_cast<double>(p.n_items);
         return;
     }
+    if (e == o_bad) return;          // counted by derive_kernel (which sums every item's counts anyway)
     for (long long i = tid; i < p.n_items; i += 256) {
         if (e < o_th) isum += static_cast<long long>(p.counts[i * K * K + (e - o_cm)]);
         else if (e < o_bs) isum += p.thick ? p.thick[i * K + (e - o_th)] : 0;
@@ -149,10 +152,6 @@ __global__ void __launch_bounds__(256) totals_kernel(const TotalsParams p) {
             uint32_t f = 0;
             for (int c = 0; c < K; ++c) f |= p.flags ? p.flags[i * K + c] : 0;
             isum += (f & (OCTM_CF_TRUE_OVERFLOW | OCTM_CF_PRED_OVERFLOW)) ? 1 : 0;
-        } else if (e == o_bad) {
-            unsigned long long px = 0;
-            for (int c = 0; c < K * K; ++c) px += p.counts[i * K * K + c];
-            isum += px != static_cast<unsigned long long>(p.item_px) ? 1 : 0;
         } else if (e < o_fl) {
             is_int = false; is_max = true;
             const double v = p.cls[(i * K + (e - o_mx)) * OCTM_NUM_CLASS_METRICS + OCTM_M_HAUSDORFF];
@@ -207,16 +206,18 @@ extern "C" int octm_derive_metrics(const uint64_t* counts, const int64_t* thick_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     octm::DeriveParams p{reinterpret_cast<const unsigned long long*>(counts), reinterpret_cast<const long long*>(thick_absdiff),
                          reinterpret_cast<const long long*>(bnd_sq), reinterpret_cast<const long long*>(bnd_abs), n_pts, max_sq,
-                         p95_sq, sum_dist, n_items, H, W, num_classes, class_metrics, boundary_metrics};
+                         p95_sq, sum_dist, n_items, H, W, num_classes, class_metrics, boundary_metrics,
+                         totals ? totals + (octm_totals_sum_len(num_classes) - 1) : nullptr};
+    if (totals != nullptr && cudaMemsetAsync(p.n_bad, 0, sizeof(double), s) != cudaSuccess)
+        return octm::fail(OCTM_ERR_LAUNCH, "memset(totals) failed");
     const long long threads = n_items * num_classes;
     if (n_items > 0) {
-        octm::derive_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(p);
+        OCTM_TIMED("derive_kernel", s) octm::derive_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(p);
         if (int e = octm::check_launch("derive_kernel")) return e;
     }
     if (totals != nullptr) {       // also for an empty batch: n_items 0, sums 0, maxima -1, flags 0
-        octm::TotalsParams t{p.counts, p.thick, p.bsq, p.babs, class_metrics, contour_flags, n_items,
-                             static_cast<long long>(H) * W, num_classes, totals};
-        octm::totals_kernel<<<octm_totals_len(num_classes), 256, 0, s>>>(t);
+        octm::TotalsParams t{p.counts, p.thick, p.bsq, p.babs, class_metrics, contour_flags, n_items, num_classes, totals};
+        OCTM_TIMED("totals_kernel", s) octm::totals_kernel<<<octm_totals_len(num_classes), 256, 0, s>>>(t);
         if (int e = octm::check_launch("totals_kernel")) return e;
     }
     return OCTM_OK;

@@ -402,17 +402,17 @@ extern "C" int octm_surface3d_u8(const uint8_t* y_true, const uint8_t* y_pred, i
             return static_cast<unsigned>(b < cap ? b : cap);
         };
         if (D2 % 16 == 0 && reinterpret_cast<uintptr_t>(p.src) % 16 == 0)
-            octm::edt3_pass1_vec_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
+            OCTM_TIMED("edt3_pass1_vec_kernel", st) octm::edt3_pass1_vec_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
         else
-            octm::edt3_pass1_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
+            OCTM_TIMED("edt3_pass1_kernel", st) octm::edt3_pass1_kernel<<<blocks(1ll * D0 * D1), 128, 0, st>>>(p);
         if (int e = octm::check_launch("edt3_pass1_kernel")) return e;
-        octm::edt3_pass2_kernel<<<blocks(1ll * D0 * D2), 128, 0, st>>>(p);
+        OCTM_TIMED("edt3_pass2_kernel", st) octm::edt3_pass2_kernel<<<blocks(1ll * D0 * D2), 128, 0, st>>>(p);
         if (int e = octm::check_launch("edt3_pass2_kernel")) return e;
-        octm::edt3_pass3_kernel<<<blocks(1ll * D1 * D2), 128, 0, st>>>(p);
+        OCTM_TIMED("edt3_pass3_kernel", st) octm::edt3_pass3_kernel<<<blocks(1ll * D1 * D2), 128, 0, st>>>(p);
         if (int e = octm::check_launch("edt3_pass3_kernel")) return e;
         // n_pts keeps the 2-D layout [K][2] = (surface voxels of y_true, of y_pred): direction 0 queries y_pred's
         octm::Sel3Params sp{hist, nbins, n_pts + cls * 2 + (1 - dir), max_sq + unit, p95_sq + 2 * unit, sum_dist + unit};
-        octm::edt3_select_kernel<<<1, 1024, 0, st>>>(sp);
+        OCTM_TIMED("edt3_select_kernel", st) octm::edt3_select_kernel<<<1, 1024, 0, st>>>(sp);
         if (int e = octm::check_launch("edt3_select_kernel")) return e;
     }
     return OCTM_OK;

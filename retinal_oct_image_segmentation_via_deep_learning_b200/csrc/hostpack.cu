@@ -100,14 +100,14 @@ extern "C" int octm_unpack_nibbles_u8(const uint8_t* packed, int64_t n_labels, u
         long long blocks = (n_vec + 255) / 256;
         const long long cap = static_cast<long long>(octm::sm_count()) * 8;
         if (blocks > cap) blocks = cap;
-        octm::unpack_nibbles_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(packed), n_vec,
+        OCTM_TIMED("unpack_nibbles_kernel", st) octm::unpack_nibbles_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(packed), n_vec,
                                                                                   reinterpret_cast<uint4*>(labels));
         if (int e = octm::check_launch("unpack_nibbles_kernel")) return e;
     }
     const long long first = n_vec * 16;
     if (first < n_packed) {
         const long long rest = n_packed - first;
-        octm::unpack_nibbles_tail_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, st>>>(packed, first, n_packed, labels, n_labels);
+        OCTM_TIMED("unpack_nibbles_tail_kernel", st) octm::unpack_nibbles_tail_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, st>>>(packed, first, n_packed, labels, n_labels);
         if (int e = octm::check_launch("unpack_nibbles_tail_kernel")) return e;
     }
     return OCTM_OK;

@@ -839,7 +839,7 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     }
     long long grid = static_cast<long long>(sm_count()) * per_sm;
     if (grid > p.n_items) grid = p.n_items;
-    kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, tm_true, tm_pred);
+    OCTM_TIMED("label_pass_fast", stream) kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, tm_true, tm_pred);
     return check_launch("label_pass_fast");
 }
 
@@ -870,7 +870,7 @@ static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
     }
     long long grid = p.n_items * strips;
     if (grid > resident) grid = resident;
-    label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p, strips);
+    OCTM_TIMED("label_pass_generic", stream) label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p, strips);
     return check_launch("label_pass_generic");
 }
 
@@ -959,7 +959,7 @@ extern "C" int octm_boundary_error_i32(const int32_t* bnd_true, const int32_t* b
     if (n_items == 0) return OCTM_OK;
     if (!bnd_true || !bnd_pred || !sum_sq || !sum_abs) return octm::fail(OCTM_ERR_INVALID, "null pointer");
     const long long rows = n_items * num_boundaries;
-    octm::boundary_error_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    OCTM_TIMED("boundary_error_kernel", static_cast<cudaStream_t>(stream)) octm::boundary_error_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         bnd_true, bnd_pred, rows, W, reinterpret_cast<long long*>(sum_sq), reinterpret_cast<long long*>(sum_abs));
     return octm::check_launch("boundary_error_kernel");
 }
@@ -969,6 +969,6 @@ extern "C" int octm_validate_labels_u8(const uint8_t* labels, int64_t n_elems, u
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(max_label, 0, sizeof(uint32_t), s) != cudaSuccess) return octm::fail(OCTM_ERR_LAUNCH, "memset failed");
     if (n_elems == 0) return OCTM_OK;
-    octm::max_label_kernel<<<148 * 8, 256, 0, s>>>(labels, n_elems, max_label);
+    OCTM_TIMED("max_label_kernel", s) octm::max_label_kernel<<<148 * 8, 256, 0, s>>>(labels, n_elems, max_label);
     return octm::check_launch("max_label_kernel");
 }

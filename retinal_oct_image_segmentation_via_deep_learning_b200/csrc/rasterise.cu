@@ -109,7 +109,7 @@ extern "C" int octm_labels_from_boundaries(const void* boundaries, int dtype, in
     const long long cap = static_cast<long long>(octm::sm_count()) * 16;
     if (grid > cap) grid = cap;
     const size_t smem = static_cast<size_t>(num_boundaries > 0 ? num_boundaries : 1) * strip * sizeof(int);
-    if (wide) octm::rasterise_kernel<4><<<static_cast<unsigned>(grid), octm::kRasterThreads, smem, st>>>(p);
-    else octm::rasterise_kernel<1><<<static_cast<unsigned>(grid), octm::kRasterThreads, smem, st>>>(p);
+    if (wide) OCTM_TIMED("rasterise_kernel", st) octm::rasterise_kernel<4><<<static_cast<unsigned>(grid), octm::kRasterThreads, smem, st>>>(p);
+    else OCTM_TIMED("rasterise_kernel", st) octm::rasterise_kernel<1><<<static_cast<unsigned>(grid), octm::kRasterThreads, smem, st>>>(p);
     return octm::check_launch("rasterise_kernel");
 }

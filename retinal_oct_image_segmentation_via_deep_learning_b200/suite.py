@@ -254,16 +254,24 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
     max_pts = (int(max_pts) + 3) & ~3          # vertices are stored in 16-byte groups
     dev = yt.device
     i32 = dict(dtype=torch.int32, device=dev)
-    numel = n * k * 2 * max_pts
+    numel = (n * k * 2 * max_pts + 63) & ~63          # 256-byte multiples (octm_contour2d_metrics_u8's workspace layout)
     # stream-ordered reuse: every consumer of the scratch is enqueued on the same stream
     scratch = None if (want_verts and want_sq) else _vertex_scratch(dev, 2 * numel)
-    verts = torch.empty((n, k, 2, max_pts), **i32) if want_verts else scratch[:numel].view(n, k, 2, max_pts)
-    sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else scratch[numel:].view(n, k, 2, max_pts)
+    nv = n * k * 2 * max_pts
+    verts = torch.empty((n, k, 2, max_pts), **i32) if want_verts else scratch[:nv].view(n, k, 2, max_pts)
+    sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else scratch[numel:numel + nv].view(n, k, 2, max_pts)
     n_pts = torch.empty((n, k, 2), **i32)
     flags = torch.empty((n, k), **i32)
     max_sq = torch.empty((n, k, 2), **i32)
     p95 = torch.empty((n, k, 2, 2), **i32)
     sums = torch.empty((n, k, 2), dtype=torch.float64, device=dev)
+    if bnd is not None and not want_verts and not want_sq:
+        # the production path: layered pairs are measured from the boundary rows, the rest through vertex lists
+        with _Timed(timers, "contour"):
+            _lib.call("octm_contour2d_metrics_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), _ptr(bnd[0]),
+                      _ptr(bnd[1]), max_pts, _ptr(n_pts), _ptr(flags), _ptr(max_sq), _ptr(p95), _ptr(sums),
+                      _ptr(scratch), scratch.numel() * 4, _stream())
+        return ContourOut(n_pts, flags, max_sq, p95, sums, None, None, max_pts)
     with _Timed(timers, "contour_trace"):
         _lib.call("octm_contour2d_trace_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos),
                   _ptr(bnd[0]) if bnd else None, _ptr(bnd[1]) if bnd else None, max_pts, _ptr(verts),
@@ -298,6 +306,11 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
                 _lib.call("octm_first_pos_u8", _ptr(src), n, h * w, k, _ptr(tmp), _stream())
                 first_pos[:, m, :] = tmp
         keep = return_vertices or return_sq
+        if n == 0:
+            i32 = dict(dtype=torch.int32, device=dev)
+            return ContourOut(torch.empty((0, k, 2), **i32), torch.empty((0, k), **i32), torch.empty((0, k, 2), **i32),
+                              torch.empty((0, k, 2, 2), **i32), torch.empty((0, k, 2), dtype=torch.float64, device=dev),
+                              None, None, max_pts)
         per_item = k * 2 * max_pts * 4 * 2          # vertices + squared-distance scratch
         chunk = n if keep else max(1, min(n, CONTOUR_CHUNK_BYTES // per_item))
         parts = []

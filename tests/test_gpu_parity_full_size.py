@@ -59,14 +59,14 @@ def _check_suite_vs_oracle(yt, yp, k, cuda, **kw):
     return n_contours
 
 
-def _check_vertices_with_boundaries(yt, yp, k, cuda):
+def _check_vertices_with_boundaries(yt, yp, k, cuda, max_pts=2048):
     """The layered emit path fed the label pass's boundary rows, vertex multisets and D2 multisets vs the oracle."""
     import torch
     from retinal_oct_image_segmentation_via_deep_learning_b200 import suite
     t, p = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
     lp = suite.label_pass(t, p, k, seeds=True, boundaries=True)
     out = suite.contour_pass(t, p, k, lp.first_pos, boundaries=(lp.bnd_true, lp.bnd_pred), return_vertices=True,
-                             return_sq=True)
+                             return_sq=True, max_pts=max_pts)
     n_pts = out.n_pts.cpu().numpy().view(np.uint32)
     verts = out.verts.cpu().numpy().view(np.uint32)
     sq = out.sq.cpu().numpy().view(np.uint32)
@@ -104,7 +104,7 @@ def test_cfg4_full_size_thin_and_touching_layers(cuda):
     _check_vertices_with_boundaries(yt, yp, 8, cuda)
     yt, yp = synth.layered_pair(2, 496, 512, 8, seed=65, min_gap=0, jitter=3.0)       # layers may vanish in places
     _check_suite_vs_oracle(yt, yp, 8, cuda)
-    _check_vertices_with_boundaries(yt, yp, 8, cuda)
+    _check_vertices_with_boundaries(yt, yp, 8, cuda, max_pts=8192)
 
 
 def test_cfg4_uniform_random_labels(cuda):
