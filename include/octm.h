@@ -122,6 +122,17 @@ OCTM_API int octm_label_pass_u8(const uint8_t* y_true, const uint8_t* y_pred, in
                        int64_t* bnd_abs, int32_t* bnd_true, int32_t* bnd_pred, uint32_t* first_pos,
                        void* stream);
 
+/* The full pass (all outputs above required except the boundary rows) plus a per-item certificate of LAYERING:
+ *   unsorted  uint32 [n] : bit 0 / bit 1 set when some column of y_true / y_pred is not non-decreasing from top to
+ *                          bottom (0 = every A-scan of both maps crosses the classes in order).  For an item with
+ *                          unsorted == 0 every class contour is a function of the boundary rows alone, which is what
+ *                          lets octm_contour2d_metrics_u8 measure it without reading the label maps again.
+ *                          Items taller than 504 rows are reported as unsorted (not certified). */
+OCTM_API int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                              int num_classes, uint64_t* counts, int64_t* thick_absdiff, int64_t* bnd_sq,
+                              int64_t* bnd_abs, int32_t* bnd_true, int32_t* bnd_pred, uint32_t* first_pos,
+                              uint32_t* unsorted, void* stream);
+
 /* Which implementation octm_label_pass_u8 / K1 / K2 would use for this shape:
  * 1 = TMA-staged column-strip kernel, 0 = generic kernel. */
 OCTM_API int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred);
@@ -162,16 +173,19 @@ OCTM_API int octm_contour2d_u8(const uint8_t* y_true, const uint8_t* y_pred, int
                       uint32_t* p95_sq, double* sum_dist, void* workspace, size_t workspace_bytes,
                       void* stream);
 
-/* The same metrics for callers that ran octm_label_pass_u8 first (the batched suite does): first_pos AND the boundary
- * rows bnd_true / bnd_pred [n][K-1][W] (may both be NULL) are handed in.  Pairs whose two contours are height
- * functions over the columns -- verified against the label maps, the case of layered retinas -- are measured
- * straight from the boundary rows in shared memory: their vertex lists never reach HBM.  Everything else (blobs,
- * broken or touching layers, stray pixels above a layer) goes through the vertex lists like octm_contour2d_u8.
- * Identical outputs either way.  workspace: 2 * round_up(n * K * 2 * max_pts * 4, 256) bytes (vertices + d2). */
+/* The same metrics for callers that ran octm_label_pass_sorted_u8 first (the batched suite does): first_pos, the
+ * boundary rows bnd_true / bnd_pred [n][K-1][W] and the label pass's layering certificate `unsorted` [n] are handed in
+ * (bnd_* and unsorted may be NULL: everything then goes through vertex lists like octm_contour2d_u8).
+ * On an item whose columns are all in class order, contour [0] of a class mask is a height function over the columns
+ * exactly when a few inequalities between neighbouring boundary rows hold; such pairs are verified AND measured from
+ * the boundary rows in shared memory: neither the label maps nor any vertex list are touched again.  Everything else
+ * (blobs, broken or touching layers, stray pixels) is verified against the label pixels, walked, and searched through
+ * vertex lists.  Identical outputs either way.
+ * workspace: 2 * round_up(n * K * 2 * max_pts * 4, 256) + 256 bytes (vertices, d2, one counter). */
 OCTM_API int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
                               int num_classes, const uint32_t* first_pos, const int32_t* bnd_true,
-                              const int32_t* bnd_pred, int max_pts, uint32_t* n_pts, uint32_t* flags,
-                              uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, void* workspace,
+                              const int32_t* bnd_pred, const uint32_t* unsorted, int max_pts, uint32_t* n_pts,
+                              uint32_t* flags, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, void* workspace,
                               size_t workspace_bytes, void* stream);
 
 /* The two stages of the above, exposed for tests and for callers that want the vertices.

@@ -38,11 +38,12 @@ SIGNATURES = {
     "octm_column_scan_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P]),
     "octm_boundary_error_i32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "octm_label_pass_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "octm_label_pass_sorted_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "octm_label_pass_path": (_INT, [_INT, _INT, _INT, _P, _P]),
     "octm_validate_labels_u8": (_INT, [_P, _I64, _P, _P]),
     "octm_contour2d_workspace_bytes": (_c.c_size_t, [_I64, _INT, _INT, _INT, _INT]),
     "octm_contour2d_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _INT, _P, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
-    "octm_contour2d_metrics_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
+    "octm_contour2d_metrics_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
     "octm_first_pos_u8": (_INT, [_P, _I64, _I64, _INT, _P, _P]),
     "octm_contour2d_trace_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _INT, _P, _P, _P, _P]),
     "octm_contour2d_distance": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _INT, _P]),

@@ -42,6 +42,7 @@ struct TraceParams {
     const int* bnd_t;            // [n][K-1][W] #{label < k} per column of y_true (label pass), or null
     const int* bnd_p;
     bool only_todo;              // walk only the contours trace_layered_kernel left (n_pts == kTraceTodo)
+    const uint32_t* todo_count;  // device word: contours / units left for the fallback kernels; 0 = nothing to do (or null)
 };
 
 constexpr uint32_t kTraceTodo = 0xffffffffu;
@@ -87,6 +88,7 @@ __device__ __forceinline__ uint32_t label_of(const uint4& w, uint32_t c) {
 template <bool WORDS>
 __global__ void __launch_bounds__(128, OCTM_TRACE_MINB) trace_kernel(const TraceParams prm) {
     __shared__ uint32_t s_step[64];      // step_word table: (case, entry edge) -> exit edge, vertex offset, order
+    if (prm.todo_count != nullptr && *prm.todo_count == 0) return;
     if (threadIdx.x < 64) s_step[threadIdx.x] = step_word(threadIdx.x);
     __syncthreads();
     const int K = prm.K, H = prm.H, W = prm.W;
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
     const int K = prm.K, H = prm.H, W = prm.W;
     const uint32_t cap = static_cast<uint32_t>(prm.max_pts);
     const long long total = prm.n_items * K * 2, per_map = prm.n_items * K;
+    if (prm.todo_count != nullptr && *prm.todo_count == 0) return;
     for (long long gid = static_cast<long long>(blockIdx.x) * 4 + warp; gid < total; gid += static_cast<long long>(gridDim.x) * 4) {
         const int m = gid >= per_map ? 1 : 0;
         const long long rem = gid - m * per_map;
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
         const uint8_t* L = (m ? prm.yp : prm.yt) + item * H * static_cast<long long>(W);
         uint32_t* out = prm.verts + ((item * K + cls) * 2 + m) * static_cast<long long>(cap);
         uint32_t* np = prm.n_pts + (item * K + cls) * 2 + m;
+        if (prm.only_todo && *np != kTraceTodo) continue;
         const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
         // one load for all seeds; the class at pixel (0, 0) is the one whose first occurrence is index 0
         const uint32_t myfp = lane < K ? fp[lane] : OCTM_NO_SEED;
@@ -676,6 +680,7 @@ struct SearchParams {
     double* sum_dist;        // [n][K][2]
     bool keep_d2;            // store every unit's squared distances as well
     bool only_marked;        // search only the units whose max_sq is kNeedsSearch
+    const uint32_t* todo_count;
 };
 
 constexpr int kCountBins = 1024;                    // squared distances 0, 2, .. 2046 are counted in shared memory
@@ -764,6 +769,7 @@ __global__ void __launch_bounds__(kSearchThreads, OCTM_SEARCH_MINB) distance_sea
     __shared__ int s_next;
     __shared__ uint32_t s_bins[kCountBins / 2];      // two 16-bit counters per word: count of squared distance 2 * h
     __shared__ uint32_t s_vmax, s_big;
+    if (prm.todo_count != nullptr && *prm.todo_count == 0) return;
     for (int i = threadIdx.x; i < kCountBins / 2; i += kSearchThreads) s_bins[i] = 0;
     if (threadIdx.x == 0) s_vmax = s_big = 0;
     const int cap = prm.max_pts, tile = prm.tile;
@@ -936,6 +942,7 @@ struct ColumnParams {
     double* sum_dist;        // [n][K][2]
     bool keep_d2;
     bool only_marked;        // search only the units whose max_sq is kNeedsSearch (the rest is already finished)
+    const uint32_t* todo_count;   // device word: 0 = no unit is marked, leave at once (or null)
 };
 
 // Query groups: kColGroup consecutive lanes share one column span (their sources are read from one address per
@@ -1070,6 +1077,7 @@ __global__ void __launch_bounds__(kColThreads, OCTM_COL_MINB) distance_column_ke
     __shared__ uint32_t s_vmax, s_big;
     __shared__ uint32_t s_wtot[kColThreads / 32];
     const int cap = prm.max_pts, ncol = prm.ncol;
+    if (prm.todo_count != nullptr && *prm.todo_count == 0) return;
     int4* const src = reinterpret_cast<int4*>(dsm);                                                 // cap + 4 entries
     uint32_t* const col = reinterpret_cast<uint32_t*>(dsm + (static_cast<size_t>(cap) + 4) * 16);   // ncol + 1 entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1223,6 +1231,7 @@ struct SelectParams {
     uint32_t* max_sq;        // [n][K][2]
     uint32_t* p95_sq;        // [n][K][2][2]
     double* sum_dist;        // [n][K][2]
+    const uint32_t* todo_count;
 };
 
 // k-th smallest (0-based) of vals[0..m): 8-bit radix passes over a warp-private histogram; every lane
@@ -1281,6 +1290,7 @@ __global__ void __launch_bounds__(128) distance_select_kernel(const SelectParams
     __shared__ uint32_t s_hist[4][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cap = prm.max_pts;
+    if (prm.todo_count != nullptr && *prm.todo_count == 0) return;
     for (long long unit = static_cast<long long>(blockIdx.x) * 4 + warp; unit < prm.n_units;
          unit += static_cast<long long>(gridDim.x) * 4) {
         const long long pair = unit >> 1;
@@ -1357,7 +1367,7 @@ __global__ void __launch_bounds__(128) distance_select_kernel(const SelectParams
 // vertices emitted from the tables (column order) and both units marked kNeedsSearch for distance_column_kernel.
 constexpr int kLdWarps = 4;           // one CTA = one (item, class) pair: the tables are shared, the query blocks dealt out
 constexpr int kLdPad = 32;            // empty columns on both sides of a table: the scan needs no clamping up to d = 32
-constexpr int kLdRing = 256;          // odd-column query ring per warp (entries)
+constexpr int kLdRing = 512;          // odd-column query ring per warp (entries)
 #ifndef OCTM_LD_MINB
 #define OCTM_LD_MINB 10
 #endif
@@ -1366,48 +1376,67 @@ struct LayeredDistParams {
     const uint32_t* first_pos;   // [n][2][K]
     const int* bnd_t;            // [n][K-1][W]
     const int* bnd_p;
+    const uint32_t* unsorted;    // [n] bit m: map m of the item has a column that is not in class order (label pass)
     long long n_pairs;           // n * K
-    int W, K, max_pts;
+    int H, W, K, max_pts;
     int tab;                     // int16 entries per table: 2 W - 1 + 2 kLdPad, rounded up to a multiple of 8
     uint32_t* verts;             // [n][K][2][max_pts]  written only for pairs left to the vertex-list search
-    uint32_t* n_pts;             // [n][K][2]  in: count | kLayeredBit, kTraceTodo or 0;  out: kLayeredBit cleared
-    uint32_t* max_sq;            // [n][K][2]
+    uint32_t* n_pts;             // [n][K][2]  out: vertex count, 0 (no contour) or kTraceTodo (left to the fallback kernels)
+    uint32_t* max_sq;            // [n][K][2]  out; kNeedsSearch for the units left to the vertex-list search
     uint32_t* p95_sq;            // [n][K][2][2]
     double* sum_dist;            // [n][K][2]
+    uint32_t* todo_count;        // += 1 per pair left to the fallback kernels (zeroed by the host)
 };
 
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
 __device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
 
-// nearest vertex of the tabulated contour (lo / hi point at column 0 of the tables) to the query (qy, qx)
-__device__ __forceinline__ int layered_nearest(const short* lo, const short* hi, int qy, int qx, int ncol) {
-    const short* l0 = lo + qx;
-    const short* h0 = hi + qx;
-    const int dy0 = max3i(l0[0] - qy, qy - h0[0], 0);
-    int best = dy0 * dy0;
+// Nearest vertices of the tabulated contour (lo / hi point at column 0 of the tables) to TWO queries per lane: the
+// two scans share one loop (twice the loads in flight per pass, half the loop overhead per query).  A query whose
+// scan is over keeps folding in real distances, which is harmless.
+__device__ __forceinline__ void layered_nearest2(const short* lo, const short* hi, int qy0, int qx0, int qy1, int qx1,
+                                                 int ncol, int& best0, int& best1) {
+    const short* l0 = lo + qx0;
+    const short* h0 = hi + qx0;
+    const short* l1 = lo + qx1;
+    const short* h1 = hi + qx1;
+    const int dy0 = max3i(l0[0] - qy0, qy0 - h0[0], 0), dy1 = max3i(l1[0] - qy1, qy1 - h1[0], 0);
+    best0 = dy0 * dy0;
+    best1 = dy1 * dy1;
     int d = 1;
     // columns qx -+ d, two distances per pass (odd d: the other row parity, a miss by at least one row)
-    while (d * d < best && d < kLdPad) {
-        const int a0 = max3i(l0[-d] - qy, qy - h0[-d], 1), a1 = max3i(l0[d] - qy, qy - h0[d], 1);
-        const int b0 = max3i(l0[-d - 1] - qy, qy - h0[-d - 1], 0), b1 = max3i(l0[d + 1] - qy, qy - h0[d + 1], 0);
+    while (d * d < max(best0, best1) && d < kLdPad) {
         const int d2 = d * d, e2 = (d + 1) * (d + 1);
-        best = min3i(best, a0 * a0 + d2, a1 * a1 + d2);
-        best = min3i(best, b0 * b0 + e2, b1 * b1 + e2);
+        {
+            const int a0 = max3i(l0[-d] - qy0, qy0 - h0[-d], 1), a1 = max3i(l0[d] - qy0, qy0 - h0[d], 1);
+            const int b0 = max3i(l0[-d - 1] - qy0, qy0 - h0[-d - 1], 0), b1 = max3i(l0[d + 1] - qy0, qy0 - h0[d + 1], 0);
+            best0 = min3i(best0, a0 * a0 + d2, a1 * a1 + d2);
+            best0 = min3i(best0, b0 * b0 + e2, b1 * b1 + e2);
+        }
+        {
+            const int a0 = max3i(l1[-d] - qy1, qy1 - h1[-d], 1), a1 = max3i(l1[d] - qy1, qy1 - h1[d], 1);
+            const int b0 = max3i(l1[-d - 1] - qy1, qy1 - h1[-d - 1], 0), b1 = max3i(l1[d + 1] - qy1, qy1 - h1[d + 1], 0);
+            best1 = min3i(best1, a0 * a0 + d2, a1 * a1 + d2);
+            best1 = min3i(best1, b0 * b0 + e2, b1 * b1 + e2);
+        }
         d += 2;
     }
     // contours further apart than the pad (rare): the same scan with clamped columns (the pads are empty columns)
-    for (; d * d < best; ++d) {
-        const int cl = max(qx - d, -1), cr = min(qx + d, ncol);
-        const int par = d & 1;
-        const int a0 = max3i(lo[cl] - qy, qy - hi[cl], par), a1 = max3i(lo[cr] - qy, qy - hi[cr], par);
-        best = min3i(best, a0 * a0 + d * d, a1 * a1 + d * d);
+    for (int e = d; e * e < best0; ++e) {
+        const int cl = max(qx0 - e, -1), cr = min(qx0 + e, ncol), par = e & 1;
+        const int a0 = max3i(lo[cl] - qy0, qy0 - hi[cl], par), a1 = max3i(lo[cr] - qy0, qy0 - hi[cr], par);
+        best0 = min3i(best0, a0 * a0 + e * e, a1 * a1 + e * e);
     }
-    return best;
+    for (int e = d; e * e < best1; ++e) {
+        const int cl = max(qx1 - e, -1), cr = min(qx1 + e, ncol), par = e & 1;
+        const int a0 = max3i(lo[cl] - qy1, qy1 - hi[cl], par), a1 = max3i(lo[cr] - qy1, qy1 - hi[cr], par);
+        best1 = min3i(best1, a0 * a0 + e * e, a1 * a1 + e * e);
+    }
 }
 
 __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_kernel(const LayeredDistParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
-    __shared__ uint32_t s_vmax[2], s_bad;
+    __shared__ uint32_t s_vmax[2], s_bad, s_ok[2], s_minkey[2], s_cnt[2], s_seed[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = prm.W, K = prm.K, tab = prm.tab, ncol = 2 * W - 1;
     short* const tabs = reinterpret_cast<short*>(dsm);                                   // [map][lo | hi][tab]
@@ -1421,55 +1450,103 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
             tabs[(2 * m + 1) * tab + j] = -32768;
         }
     }
-    const int nblk = (W + 31) >> 5;
+    const int nblk = (W + 63) >> 6;
 
     for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
         __syncthreads();                     // the previous pair is finished with the tables, the counters and s_*
         const long long item = pair / K;
         const int cls = static_cast<int>(pair - item * K);
-        const uint32_t n0 = prm.n_pts[pair * 2], n1 = prm.n_pts[pair * 2 + 1];
-        const bool lay0 = n0 != kTraceTodo && (n0 & kLayeredBit), lay1 = n1 != kTraceTodo && (n1 & kLayeredBit);
-        const uint32_t cnt0 = n0 & ~kLayeredBit, cnt1 = n1 & ~kLayeredBit;
-        if (n0 == 0 || n1 == 0) {            // a mask without a contour: nothing to measure (reference: IndexError)
-            if (tid < 2) {
-                const uint32_t n = tid ? n1 : n0;
-                prm.n_pts[pair * 2 + tid] = n != kTraceTodo ? (n & ~kLayeredBit) : n;
-                prm.max_sq[pair * 2 + tid] = (n0 == kTraceTodo || n1 == kTraceTodo) ? kNeedsSearch : 0u;
-                prm.p95_sq[pair * 4 + tid * 2] = prm.p95_sq[pair * 4 + tid * 2 + 1] = 0;
-                prm.sum_dist[pair * 2 + tid] = 0.0;
-            }
-            continue;
-        }
-        if (tid < 2) s_vmax[tid] = 0;
+        if (tid < 2) { s_vmax[tid] = 0; s_ok[tid] = 1; s_minkey[tid] = 0xffffffffu; s_cnt[tid] = 0; }
         if (tid == 2) s_bad = 0;
-        // ---- tables of the verified sides: warps 0-1 map 0, warps 2-3 map 1
+        const uint32_t unsorted = prm.unsorted[item];
+        __syncthreads();
+        // ---- verification + tables, warps 0-1: map 0, warps 2-3: map 1.  On a map whose columns are all in class
+        // order (the label pass's certificate) contour [0] of a class mask is the height function h(x) = #{label <
+        // k} of one boundary row iff  (a) 1 <= h <= H - 1,  (b) wherever the polyline steps between neighbouring
+        // columns the class really lies on its side of the step -- a condition on the NEXT boundary row (band not
+        // thinner than the step) or, for the class of pixel (0, 0), on the previous one --, and (c) the raster-first
+        // pixel of the path is the seed the label pass found.  All of it is arithmetic on the boundary rows: what
+        // trace_layered_kernel establishes by reading label pixels, without touching the label maps.
         {
             const int m = warp >> 1;
-            if (m ? lay1 : lay0) {
-                const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
-                const uint32_t myfp = lane < K ? fp[lane] : OCTM_NO_SEED;
-                const int c00 = __ffs(__ballot_sync(0xffffffffu, myfp == 0u)) - 1;
-                const int brow = cls == c00 ? cls : cls - 1;                   // as in trace_layered_kernel
-                const int* hrow = (m ? prm.bnd_p : prm.bnd_t) + (item * (K - 1) + brow) * static_cast<long long>(W);
+            const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
+            const uint32_t myfp = lane < K ? fp[lane] : OCTM_NO_SEED;
+            const int c00 = __ffs(__ballot_sync(0xffffffffu, myfp == 0u)) - 1;
+            const bool inv = cls == c00;                                   // the class is the region above the path
+            const uint32_t others = __reduce_min_sync(0xffffffffu, lane == c00 ? OCTM_NO_SEED : myfp);
+            const uint32_t seed = inv ? others : __shfl_sync(0xffffffffu, myfp, cls);
+            if (lane == 0 && (warp & 1) == 0) s_seed[m] = seed;
+            const int brow = inv ? cls : cls - 1;
+            if (seed != OCTM_NO_SEED && !((unsorted >> m) & 1u) && brow >= 0 && brow < K - 1) {
+                const int* rows = (m ? prm.bnd_p : prm.bnd_t) + item * (K - 1) * static_cast<long long>(W);
+                const int* hrow = rows + brow * static_cast<long long>(W);
+                // the row that bounds the class on the far side of the path: the next boundary (band thickness) for a
+                // class below the path, the previous one for the class of pixel (0, 0); null = nothing to check
+                const int* orow = inv ? (cls > 0 ? rows + (cls - 1) * static_cast<long long>(W) : nullptr)
+                                      : (cls < K - 1 ? rows + cls * static_cast<long long>(W) : nullptr);
                 uint32_t* lo32 = reinterpret_cast<uint32_t*>(tabs + (2 * m) * tab + kLdPad);
                 uint32_t* hi32 = lo32 + (tab >> 1);
+                bool ok = true;
+                uint32_t minkey = 0xffffffffu, steps = 0;
+                const int H = prm.H;
                 for (int x0 = (warp & 1) * 32; x0 < W; x0 += 64) {
                     const int x = x0 + lane;
-                    const int h = hrow[min(x, W - 1)];
-                    int hn = __shfl_down_sync(0xffffffffu, h, 1);
-                    if (lane == 31) hn = hrow[min(x + 1, W - 1)];
-                    if (x < W) {             // columns 2 x and 2 x + 1 as one 32-bit store per table (column 2 W - 1 is a pad)
+                    const int xc = min(x, W - 1);
+                    const int h = hrow[xc];
+                    int hl = __shfl_up_sync(0xffffffffu, h, 1), hn = __shfl_down_sync(0xffffffffu, h, 1);
+                    if (lane == 0) hl = hrow[max(xc - 1, 0)];
+                    if (lane == 31) hn = hrow[min(xc + 1, W - 1)];
+                    if (x >= W - 1) hn = h;
+                    const int o = orow != nullptr ? orow[xc] : (inv ? 0 : H);
+                    if (x < W) {
+                        const int lo_w = min(hl, min(h, hn)), hi_w = max(hl, max(h, hn));
+                        ok = ok && h >= 1 && h <= H - 1 && (inv ? o <= lo_w - 1 : o >= hi_w + 1);
+                        minkey = min(minkey, static_cast<uint32_t>(h) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x));
+                        steps += static_cast<uint32_t>(abs(hn - h));
+                        // columns 2 x and 2 x + 1 as one 32-bit store per table (column 2 W - 1 is a pad)
                         const uint32_t e = static_cast<uint32_t>(2 * h - 1) & 0xffffu;
-                        const bool run = x + 1 < W && hn != h;
-                        const uint32_t ol = run ? static_cast<uint32_t>(2 * min(h, hn)) : 32767u;
+                        const bool run = hn != h;
+                        const uint32_t ol = run ? static_cast<uint32_t>(2 * min(h, hn)) & 0xffffu : 32767u;
                         const uint32_t oh = run ? static_cast<uint32_t>(2 * max(h, hn) - 2) & 0xffffu : 0x8000u;
                         lo32[x] = e | (ol << 16);
                         hi32[x] = e | (oh << 16);
                     }
                 }
+                ok = __all_sync(0xffffffffu, ok);
+                minkey = __reduce_min_sync(0xffffffffu, minkey);
+                steps = __reduce_add_sync(0xffffffffu, steps);
+                if (lane == 0) {
+                    if (!ok) s_ok[m] = 0;
+                    atomicMin(&s_minkey[m], minkey);
+                    atomicAdd(&s_cnt[m], steps);
+                }
+            } else if (lane == 0) {
+                s_ok[m] = 0;
             }
         }
         __syncthreads();
+        // per map: 0 = no contour, count = verified height function, kTraceTodo = left to the fallback kernels
+        uint32_t n0, n1;
+        {
+            const uint32_t c0 = static_cast<uint32_t>(W) + s_cnt[0], c1 = static_cast<uint32_t>(W) + s_cnt[1];
+            n0 = s_seed[0] == OCTM_NO_SEED ? 0u
+                 : (s_ok[0] && s_minkey[0] == s_seed[0] && c0 <= static_cast<uint32_t>(prm.max_pts) ? c0 : kTraceTodo);
+            n1 = s_seed[1] == OCTM_NO_SEED ? 0u
+                 : (s_ok[1] && s_minkey[1] == s_seed[1] && c1 <= static_cast<uint32_t>(prm.max_pts) ? c1 : kTraceTodo);
+        }
+        const bool lay0 = n0 != 0 && n0 != kTraceTodo, lay1 = n1 != 0 && n1 != kTraceTodo;
+        const uint32_t cnt0 = n0, cnt1 = n1;
+        if (n0 == 0 || n1 == 0) {            // a mask without a contour: nothing to measure (reference: IndexError)
+            const bool todo = n0 == kTraceTodo || n1 == kTraceTodo;       // the other side is still walked for its n_pts
+            if (tid < 2) {
+                prm.n_pts[pair * 2 + tid] = tid ? n1 : n0;
+                prm.max_sq[pair * 2 + tid] = todo ? kNeedsSearch : 0u;
+                prm.p95_sq[pair * 4 + tid * 2] = prm.p95_sq[pair * 4 + tid * 2 + 1] = 0;
+                prm.sum_dist[pair * 2 + tid] = 0.0;
+            }
+            if (todo && tid == 0) atomicAdd(prm.todo_count, 1u);
+            continue;
+        }
         bool done = lay0 && lay1;            // CTA-uniform
         if (done) {
             for (int dir = 0; dir < 2; ++dir) {
@@ -1481,16 +1558,24 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
                 uint32_t* bins = bins2 + dir * (kCountBins / 2);
                 uint32_t run_max = 0, head = 0, tail = 0;
                 bool run_bad = false;
-                for (int blk = warp; blk < nblk; blk += kLdWarps) {
-                    const int x = blk * 32 + lane;
-                    const bool valid = x < W;
-                    // the even-column vertex of column x
-                    const int best = valid ? layered_nearest(slo, shi, qlo[2 * x], 2 * x, ncol) : 0;
-                    count_minima(best, valid, lane, bins, run_max, run_bad);
-                    // the run between columns x and x + 1 joins the ring
-                    const bool hasrun = valid && x + 1 < W;
-                    const int rl = hasrun ? qlo[2 * x + 1] : 32767, rh = hasrun ? qhi[2 * x + 1] : -32768;
-                    const uint32_t len = rh >= rl ? static_cast<uint32_t>((rh - rl) >> 1) + 1u : 0u;
+                // a query that costs nothing (its own column of the source: distance 0 at d = 0) for idle slots
+                const int idle_y = slo[0];
+                for (int blk = warp; blk < nblk; blk += kLdWarps) {          // 64 columns: lane takes x and x + 32
+                    const int xa = blk * 64 + lane, xb = xa + 32;
+                    const bool va = xa < W, vb = xb < W;
+                    // the even-column vertices of the two columns
+                    int ba, bb;
+                    layered_nearest2(slo, shi, va ? qlo[2 * xa] : idle_y, va ? 2 * xa : 0, vb ? qlo[2 * xb] : idle_y, vb ? 2 * xb : 0,
+                                     ncol, ba, bb);
+                    count_minima(ba, va, lane, bins, run_max, run_bad);
+                    count_minima(bb, vb, lane, bins, run_max, run_bad);
+                    // the runs between columns x and x + 1 join the ring
+                    const bool ra = xa + 1 < W, rb = xb + 1 < W;
+                    const int la = ra ? qlo[2 * xa + 1] : 32767, ha = ra ? qhi[2 * xa + 1] : -32768;
+                    const int lb = rb ? qlo[2 * xb + 1] : 32767, hb = rb ? qhi[2 * xb + 1] : -32768;
+                    const uint32_t lena = ha >= la ? static_cast<uint32_t>((ha - la) >> 1) + 1u : 0u;
+                    const uint32_t lenb = hb >= lb ? static_cast<uint32_t>((hb - lb) >> 1) + 1u : 0u;
+                    const uint32_t len = lena + lenb;
                     uint32_t incl = len;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -1498,25 +1583,35 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
                         if (lane >= o) incl += up;
                     }
                     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total > static_cast<uint32_t>(kLdRing - 32)) { run_bad = true; break; }   // absurdly steep: general path
+                    if (total > static_cast<uint32_t>(kLdRing - 64)) { run_bad = true; break; }   // absurdly steep: general path
                     uint32_t at = tail + incl - len;
-                    for (uint32_t t = 0; t < len; ++t, ++at)
-                        ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(rl + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * x + 1);
+                    for (uint32_t t = 0; t < lena; ++t, ++at)
+                        ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(la + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xa + 1);
+                    for (uint32_t t = 0; t < lenb; ++t, ++at)
+                        ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(lb + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xb + 1);
                     tail += total;
                     __syncwarp();
-                    while (tail - head >= 32u) {
-                        const uint32_t q = ring[(head + lane) & (kLdRing - 1)];
-                        head += 32u;
-                        const int b = layered_nearest(slo, shi, static_cast<int>(q >> 16), static_cast<int>(q & 0xffffu), ncol);
-                        count_minima(b, true, lane, bins, run_max, run_bad);
+                    while (tail - head >= 64u) {
+                        const uint32_t q0 = ring[(head + lane) & (kLdRing - 1)], q1 = ring[(head + 32 + lane) & (kLdRing - 1)];
+                        head += 64u;
+                        int b0, b1;
+                        layered_nearest2(slo, shi, static_cast<int>(q0 >> 16), static_cast<int>(q0 & 0xffffu), static_cast<int>(q1 >> 16),
+                                         static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
+                        count_minima(b0, true, lane, bins, run_max, run_bad);
+                        count_minima(b1, true, lane, bins, run_max, run_bad);
                     }
                     __syncwarp();
                 }
                 if (tail != head) {
-                    const bool v = static_cast<uint32_t>(lane) < tail - head;
-                    const uint32_t q = ring[(head + (v ? lane : 0)) & (kLdRing - 1)];
-                    const int b = layered_nearest(slo, shi, static_cast<int>(q >> 16), static_cast<int>(q & 0xffffu), ncol);
-                    count_minima(b, v, lane, bins, run_max, run_bad);
+                    const uint32_t left = tail - head;
+                    const bool v0 = static_cast<uint32_t>(lane) < left, v1 = static_cast<uint32_t>(lane) + 32u < left;
+                    const uint32_t q0 = ring[(head + (v0 ? lane : 0)) & (kLdRing - 1)];
+                    const uint32_t q1 = v1 ? ring[(head + 32 + lane) & (kLdRing - 1)] : q0;
+                    int b0, b1;
+                    layered_nearest2(slo, shi, static_cast<int>(q0 >> 16), static_cast<int>(q0 & 0xffffu), static_cast<int>(q1 >> 16),
+                                     static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
+                    count_minima(b0, v0, lane, bins, run_max, run_bad);
+                    count_minima(b1, v1, lane, bins, run_max, run_bad);
                 }
                 publish_counts(run_max, run_bad, lane, &s_vmax[dir], &s_bad);
             }
@@ -1555,8 +1650,11 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
                 base += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (lane == 0) prm.n_pts[pair * 2 + m] = m ? cnt1 : cnt0;
+        } else if (warp < 2 && lane == 0) {
+            prm.n_pts[pair * 2 + warp] = kTraceTodo;
         }
         if (tid >= 64 && tid < 66) prm.max_sq[pair * 2 + (tid - 64)] = kNeedsSearch;
+        if (tid == 66) atomicAdd(prm.todo_count, 1u);
     }
 }
 
@@ -1654,7 +1752,7 @@ static size_t dist_smem(int max_pts) {
 
 static int run_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes, int max_pts, int H,
                         int W, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, uint32_t* d2, int keep_d2,
-                        bool only_marked, void* stream) {
+                        bool only_marked, const uint32_t* todo_count, void* stream) {
     if (n_items < 0 || num_classes < 1 || max_pts < 8) return octm::fail(OCTM_ERR_INVALID, "bad shape");
     if (H < 1 || W < 1 || H > 8192 || W > 8192) return octm::fail(OCTM_ERR_INVALID, "H, W outside [1, 8192]");
     if (n_items == 0) return OCTM_OK;
@@ -1674,7 +1772,7 @@ static int run_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long n_pairs = n_items * num_classes;
     auto run_select = [&]() -> int {
-        octm::SelectParams kp{n_pts, d2, n_pairs * 2, max_pts, max_sq, p95_sq, sum_dist};
+        octm::SelectParams kp{n_pts, d2, n_pairs * 2, max_pts, max_sq, p95_sq, sum_dist, todo_count};
         long long kgrid = (n_pairs * 2 + 3) / 4;
         const long long kcap = static_cast<long long>(octm::sm_count()) * 16;
         if (kgrid > kcap) kgrid = kcap;
@@ -1691,7 +1789,7 @@ static int run_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_
             if (cudaFuncSetAttribute(octm::distance_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)) != cudaSuccess)
                 return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_column_kernel) failed");
-            octm::ColumnParams cp{verts, n_pts, n_pairs * 2, max_pts, ncol, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0, only_marked};
+            octm::ColumnParams cp{verts, n_pts, n_pairs * 2, max_pts, ncol, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0, only_marked, todo_count};
             long long grid = n_pairs * 2;
             const long long cap = static_cast<long long>(octm::sm_count()) * 32;
             if (grid > cap) grid = cap;
@@ -1711,7 +1809,7 @@ static int run_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_
         if (cudaFuncSetAttribute(octm::distance_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(distance_search_kernel) failed");
-        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0, only_marked};
+        octm::SearchParams sp{verts, n_pts, n_pairs * 2, max_pts, tile, d2, max_sq, p95_sq, sum_dist, keep_d2 != 0, only_marked, todo_count};
         long long grid = n_pairs * 2;
         const long long cap = static_cast<long long>(octm::sm_count()) * 32;
         if (grid > cap) grid = cap;
@@ -1736,43 +1834,42 @@ static int run_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_
 extern "C" int octm_contour2d_distance(const uint32_t* verts, const uint32_t* n_pts, int64_t n_items, int num_classes,
                                        int max_pts, int H, int W, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
                                        uint32_t* d2, int keep_d2, void* stream) {
-    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, keep_d2, false, stream);
+    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, keep_d2, false, nullptr, stream);
 }
 
 extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
                                          int num_classes, const uint32_t* first_pos, const int32_t* bnd_true,
-                                         const int32_t* bnd_pred, int max_pts, uint32_t* n_pts, uint32_t* flags,
-                                         uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
+                                         const int32_t* bnd_pred, const uint32_t* unsorted, int max_pts, uint32_t* n_pts,
+                                         uint32_t* flags, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
     if (int e = check_shape(n_items, H, W, num_classes, max_pts)) return e;
     if (n_items == 0) return OCTM_OK;
     if (!y_true || !y_pred || !first_pos || !n_pts || !flags || !max_sq || !p95_sq || !sum_dist)
         return octm::fail(OCTM_ERR_INVALID, "null pointer");
     if ((bnd_true == nullptr) != (bnd_pred == nullptr)) return octm::fail(OCTM_ERR_INVALID, "bnd_true/bnd_pred: both or neither");
     const size_t verts_b = (static_cast<size_t>(n_items) * num_classes * 2 * max_pts * sizeof(uint32_t) + 255) & ~static_cast<size_t>(255);
-    if (workspace == nullptr || workspace_bytes < 2 * verts_b)
-        return octm::fail(OCTM_ERR_WORKSPACE, "workspace too small: need %zu B", 2 * verts_b);
+    if (workspace == nullptr || workspace_bytes < 2 * verts_b + 256)
+        return octm::fail(OCTM_ERR_WORKSPACE, "workspace too small: need %zu B", 2 * verts_b + 256);
     uint32_t* verts = static_cast<uint32_t*>(workspace);
     uint32_t* d2 = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + verts_b);
+    uint32_t* todo = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + 2 * verts_b);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // OCTM_LAYERED_FUSED=0: always go through vertex lists (the round-1 path; tests compare the two)
     static const bool env_fused = [] { const char* e = getenv("OCTM_LAYERED_FUSED"); return !(e && e[0] == '0'); }();
     const int tab = (2 * W - 1 + 2 * octm::kLdPad + 7) & ~7;
     const size_t smem = static_cast<size_t>(tab) * 8 + octm::kCountBins * 4 + octm::kLdWarps * octm::kLdRing * 4;
-    const bool fused = env_fused && layered_ok(y_true, y_pred, bnd_true, bnd_pred, H, W, num_classes) && H <= 4095 &&
-                       max_pts <= 0xffff && smem <= static_cast<size_t>(octm::max_optin_smem());
+    const bool fused = env_fused && unsorted != nullptr && layered_ok(y_true, y_pred, bnd_true, bnd_pred, H, W, num_classes) &&
+                       H <= 4095 && max_pts <= 0xffff && smem <= static_cast<size_t>(octm::max_optin_smem());
     if (!fused) {
         if (int e = octm_contour2d_trace_u8(y_true, y_pred, n_items, H, W, num_classes, first_pos, bnd_true, bnd_pred, max_pts,
                                             verts, n_pts, flags, stream))
             return e;
-        return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, false, stream);
+        return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, false, nullptr, stream);
     }
-    if (cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n_items * num_classes, s) != cudaSuccess)
+    if (cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n_items * num_classes, s) != cudaSuccess ||
+        cudaMemsetAsync(todo, 0, sizeof(uint32_t), s) != cudaSuccess)
         return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
-    octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags,
-                        bnd_true, bnd_pred, false};
-    if (int e = launch_layered_trace<false>(p, s)) return e;               // verify only: n_pts = count | kLayeredBit
-    {
+    {   // every pair: boundary-row verification, and the distances of the pairs with two verified sides
         if (cudaFuncSetAttribute(octm::layered_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(layered_distance_kernel) failed");
@@ -1785,14 +1882,18 @@ extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y
         long long grid = n_pairs;
         const long long cap = static_cast<long long>(octm::sm_count()) * fit;
         if (grid > cap) grid = cap;
-        octm::LayeredDistParams lp{first_pos, bnd_true, bnd_pred, n_pairs, W, num_classes, max_pts, tab, verts, n_pts,
-                                   max_sq, p95_sq, sum_dist};
+        octm::LayeredDistParams lp{first_pos, bnd_true, bnd_pred, unsorted, n_pairs, H, W, num_classes, max_pts, tab, verts,
+                                   n_pts, max_sq, p95_sq, sum_dist, todo};
         OCTM_TIMED("layered_distance_kernel", s) octm::layered_distance_kernel<<<static_cast<unsigned>(grid), octm::kLdWarps * 32, smem, s>>>(lp);
         if (int e = octm::check_launch("layered_distance_kernel")) return e;
     }
-    p.only_todo = true;
-    if (int e = launch_walk(p, s)) return e;                                // the contours the verification rejected
-    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, true, stream);
+    // what is left (n_pts == kTraceTodo; nothing on clean layered data: the three kernels then return at once):
+    // verification against the label pixels, the walk, the vertex-list search
+    octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags,
+                        bnd_true, bnd_pred, true, todo};
+    if (int e = launch_layered_trace<true>(p, s)) return e;
+    if (int e = launch_walk(p, s)) return e;
+    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, true, todo, stream);
 }
 
 extern "C" size_t octm_contour2d_workspace_bytes(int64_t n_items, int H, int W, int num_classes, int max_pts) {

@@ -57,6 +57,7 @@ struct LabelPassParams {
     int* bnd_t;
     int* bnd_p;
     unsigned* first_pos;
+    unsigned* unsorted;   // [n] bit 0 / 1: some column of y_true / y_pred is not non-decreasing from top to bottom (or null)
     uint32_t one;   // always 1, but opaque to ptxas: `x * one + y` is then an IMAD on the (idle) FMA pipe
                     // instead of an IADD3 on the ALU pipe that the PRMT-heavy inner loop saturates
 };
@@ -67,7 +68,8 @@ constexpr int kOffWarp = 0;          // no CTA-wide block any more: warps are au
 constexpr int kWarpTotals = 2 * 8 * kStrip * 2;    // u16 [map][thr][128]
 constexpr int kWarpHist = 64 * 32 * 2;             // u16 [code][lane]
 constexpr int kWarpQueue = kQueueCap * 16;         // uint4 entries
-constexpr int kWarpBars = 256;                     // the warp's S "stage full" mbarriers (64 B) + first-position table (128 B at +128)
+constexpr int kWarpBars = 768;                     // the warp's S "stage full" mbarriers (64 B), flags (at +64), first-position
+                                                   // table (128 B at +128), last rows of the lanes' mixed passes (512 B at +256)
 constexpr int kWarpBytesShort = kWarpHist + kWarpQueue;              // H <= 504: totals alias the histogram block
 constexpr int kWarpBytesTall = kWarpHist + kWarpQueue + kWarpTotals;
 constexpr int kShortRows = 504;   // 18 byte flushes x 7 nibble flushes x 4 rows
@@ -278,13 +280,15 @@ struct StageConsts {
     unsigned short* totals;
     uint32_t* first_tab;
     uint32_t* bad;                // set when a label with bits above the 3-bit class range shows up
+    uint32_t* unsorted;           // bit 0 / 1: a column of y_true / y_pred decreases somewhere (this warp, this item)
+    uint4* prev_rows;             // [32] last row (t.x, t.y, p.x, p.y) of a lane's latest mixed pass
 };
 
 // One ring stage (rows x strip) of one consumer warp.  Each pass of the loop takes 4 rows: lanes 0-15 rows
 // (4i, 4i+2), lanes 16-31 rows (4i+1, 4i+3), 8 columns per lane, both maps.  FULL: every lane has both rows
 // (no predicates); otherwise missing rows / columns are replaced by the pad label.
 // Kept rolled: one pass is ~100 instructions and must stay inside the L0 instruction cache.
-template <int NP, bool CONF, bool COLS, bool SEEDS, bool FULL>
+template <int NP, bool CONF, bool COLS, bool SEEDS, bool SORT, bool FULL>
 __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint32_t pos, int rows, const StageConsts& sc) {
     const int npairs = (rows + 3) >> 2;
 #pragma unroll 1
@@ -321,6 +325,31 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
             if (uni && !changed) ls.run += 16u;
             const bool mixed_lane = FULL ? !uni : (va || vb);
             if (__any_sync(0xffffffffu, mixed_lane || changed)) {
+                if (SORT && (mixed_lane || changed)) {
+                    // Column order, part 1 of 2: along THIS lane's own rows (every other row of its 8 columns) the
+                    // labels must not decrease: previous row <= A <= B, bytewise, both maps.  Uniform unchanged
+                    // passes need no check (same labels as the row before); the row before a checked pass is the
+                    // open run's code, or -- after a mixed pass, which closes the run -- the copy in shared memory.
+                    // Part 2 (the two row parities interleave) is the count comparison in the item epilogue.
+                    uint32_t t0, t1, p0, p1;
+                    if (ls.last_b == 0xffffffffu) {
+                        const uint4 v = sc.prev_rows[sc.lane];
+                        t0 = v.x; t1 = v.y; p0 = v.z; p1 = v.w;
+                    } else {
+                        t0 = t1 = (ls.last_b >> 3) & 0x07070707u;
+                        p0 = p1 = ls.last_b & 0x07070707u;
+                    }
+                    const uint32_t M = 0x80808080u;       // (a | M) - b keeps bit 7 of a byte iff a >= b (labels < 128)
+                    const uint32_t gt = ((tA.x | M) - t0) & ((tA.y | M) - t1) & ((tB.x | M) - tA.x) & ((tB.y | M) - tA.y) & M;
+                    const uint32_t gp = ((pA.x | M) - p0) & ((pA.y | M) - p1) & ((pB.x | M) - pA.x) & ((pB.y | M) - pA.y) & M;
+                    if (gt != M || gp != M) atomicOr(sc.unsorted, (gt != M ? 1u : 0u) | (gp != M ? 2u : 0u));
+                    if (mixed_lane) {                     // close the run: the next pass of this lane is checked against B
+                        if (CONF && ls.last_b != 0xffffffffu) hist_add(sc.hist_lane, ls.last_b & 0x3fu, ls.run);
+                        ls.last_b = 0xffffffffu;
+                        ls.run = 0;
+                        sc.prev_rows[sc.lane] = make_uint4(tB.x, tB.y, pB.x, pB.y);
+                    }
+                }
                 if (CONF && (FULL ? high != 0 : ((va && ((tA.x | tA.y | pA.x | pA.y) & 0xf8f8f8f8u)) ||
                                         (vb && ((tB.x | tB.y | pB.x | pB.y) & 0xf8f8f8f8u)))))
                     *sc.bad = 1;                    // this warp's counts of the item are withheld (epilogue)
@@ -371,7 +400,7 @@ __device__ __forceinline__ void stage_rows(LaneState<NP>& ls, uint32_t at, uint3
 // (one box of R rows x 128 columns per map) that the warp issues for itself.  Warps of a CTA therefore
 // never wait for each other: each folds its strip's results into the zero-initialised outputs with global
 // reductions (RED.ADD / RED.MIN), so a CTA has no barrier after its start-up.
-template <int NP, bool CONF, bool COLS, bool SEEDS, bool WIDE>
+template <int NP, bool CONF, bool COLS, bool SEEDS, bool SORT, bool WIDE>
 __global__ void __launch_bounds__(WIDE ? 16 * 32 : 8 * 32, WIDE ? 1 : OCTM_LP_MINB)
 label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap tm_true, const __grid_constant__ CUtensorMap tm_pred) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -392,6 +421,8 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     const uint32_t ring_addr = bars + state_bytes;
     uint32_t* warp_first = reinterpret_cast<uint32_t*>(wbase + 128);        // [2][16] first raster position per class
     uint32_t* warp_bad = reinterpret_cast<uint32_t*>(wbase + 64);           // a label >= 8 was met in this item
+    uint32_t* warp_unsorted = reinterpret_cast<uint32_t*>(wbase + 68);      // bit 0 / 1: a column of y_true / y_pred is out of order
+    uint4* prev_rows = reinterpret_cast<uint4*>(wbase + 256);               // [32]
     if (lane == 0) {
         for (int s = 0; s < S; ++s) mbar_init_a(bars + 8 * s, 1);
         mbar_fence_init();
@@ -437,11 +468,16 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
     sc.map_bytes = map_bytes; sc.one = prm.one; sc.all_classes = ((1u << K) - 1u) * 0x101u;
     sc.phase = phase; sc.lane = lane; sc.colv = colv;
     sc.hist_lane = hist_lane; sc.queue = queue; sc.totals = totals; sc.first_tab = warp_first; sc.bad = warp_bad;
+    sc.unsorted = warp_unsorted; sc.prev_rows = prev_rows;
     LaneState<NP> ls;
     uint32_t s = 0, ph = 0;
     for (long long item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
         ls.reset(COLS);
         if (CONF && lane == 0) *warp_bad = 0;
+        if (SORT) {
+            if (lane == 0) *warp_unsorted = tall ? 3u : 0u;      // items taller than one byte-counter period: not certified
+            prev_rows[lane] = make_uint4(0, 0, 0, 0);
+        }
         if (SEEDS) warp_first[lane] = OCTM_NO_SEED;
         __syncwarp();
 
@@ -451,9 +487,9 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
             const uint32_t at = ring_addr + s * stage_bytes + lane_smem;        // this lane's first row, y_true
             const uint32_t pos = static_cast<uint32_t>(r0) * W + lane_pos;       // its raster index in the item
             if (strip_full && (rows & 3) == 0)       // warp-uniform: every lane has both of its rows
-                stage_rows<NP, CONF, COLS, SEEDS, true>(ls, at, pos, rows, sc);
+                stage_rows<NP, CONF, COLS, SEEDS, SORT, true>(ls, at, pos, rows, sc);
             else                                     // ragged strip or last rows of the item
-                stage_rows<NP, CONF, COLS, SEEDS, false>(ls, at, pos, rows, sc);
+                stage_rows<NP, CONF, COLS, SEEDS, SORT, false>(ls, at, pos, rows, sc);
             __syncwarp();                            // every lane has read the slot
             if (lane == 0 && nf_item < prm.n_items) {
                 fence_proxy_async();                 // generic reads of the slot before the async overwrite
@@ -501,6 +537,33 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
         __syncwarp();
         if (COLS) {
             ls.cs.nib_to_byte();
+            if (SORT && !tall) {
+                // Column order, part 2 of 2.  Lanes l and l ^ 16 hold the counts of the even and of the odd rows of
+                // the same 8 columns.  Each parity's rows are in order (part 1), so the whole column is in order iff
+                // for every threshold k  #{even rows below k} - #{odd rows below k} is 0 or 1  (the rows below k
+                // then form a prefix of the column).  Thresholds counted as "at or above" mirror this.
+                uint32_t viol_t = 0, viol_p = 0;
+                const bool h_even = (H & 1) == 0;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                        for (int j = 0; j < 2 * NP; ++j) {
+                            const uint32_t mine = ls.cs.byt[sl][hh][j];
+                            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 16);      // odd rows, seen from phase 0
+                            const bool below = j < kBelowThresholds;
+                            const uint32_t a = (below || !h_even) ? mine : other, b = (below || !h_even) ? other : mine;
+                            // a - b per byte must be 0 or 1; the two maps' bytes (even: y_true, odd: y_pred) are
+                            // subtracted in separate 16-bit fields with a guard bit, so that a borrow stays in its field
+                            const uint32_t G = 0x01000100u;
+                            const uint32_t dt = ((a & 0x00ff00ffu) | G) - (b & 0x00ff00ffu);
+                            const uint32_t dp = (((a >> 8) & 0x00ff00ffu) | G) - ((b >> 8) & 0x00ff00ffu);
+                            viol_t |= (dt ^ G) & 0xfffefffeu;
+                            viol_p |= (dp ^ G) & 0xfffefffeu;
+                        }
+                if (phase == 0 && (viol_t | viol_p)) atomicOr(warp_unsorted, (viol_t ? 1u : 0u) | (viol_p ? 2u : 0u));
+            }
             ls.cs.byte_to_totals(totals, lane);
             // per-column arithmetic: lane owns 4 columns of the strip
             const int lc = lane * 4;
@@ -566,6 +629,10 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
                 }
             }
         }
+        if (SORT && prm.unsorted != nullptr) {
+            __syncwarp();
+            if (lane == 0 && *warp_unsorted) atomicOr(prm.unsorted + item, *warp_unsorted);
+        }
         if (SEEDS && prm.first_pos != nullptr) {
             __syncwarp();
             const int m = lane >> 4, c = lane & 15;
@@ -586,6 +653,7 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
     __shared__ unsigned short s_cls[2][16][256];          // per-thread class counts of the current column
     __shared__ unsigned long long s_sq[16], s_abs[16], s_thick[16];
     __shared__ uint32_t s_first[2][16];
+    __shared__ uint32_t s_unsorted;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int H = prm.H, W = prm.W, K = prm.K, nthr = K - 1;
     // strips > 1 (few items): a CTA takes 256 columns of an item and adds its share to zero-initialised outputs
@@ -597,6 +665,7 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
         for (int i = tid; i < 8 * 256; i += 256) (&s_counts[0][0])[i] = 0;
         if (tid < 16) s_sq[tid] = s_abs[tid] = s_thick[tid] = 0;
         if (tid < 32) (&s_first[0][0])[tid] = OCTM_NO_SEED;
+        if (tid == 0) s_unsorted = 0;
         __syncthreads();
         const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
         const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
@@ -628,6 +697,8 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
                 const uint32_t t = bt[static_cast<long long>(y) * W + x], p = bp[static_cast<long long>(y) * W + x];
                 const uint32_t code = t * 256u + p;
                 if (code != run_code) {
+                    if (run_code != 0xffffffffu && ((t < (run_code >> 8)) || (p < (run_code & 255u))))
+                        atomicOr(&s_unsorted, (t < (run_code >> 8) ? 1u : 0u) | (p < (run_code & 255u) ? 2u : 0u));
                     flush();
                     run_code = code;
                     run = 0;
@@ -706,6 +777,7 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
             if (tid < nthr && prm.babs != nullptr && s_abs[tid])
                 atomicAdd(reinterpret_cast<unsigned long long*>(prm.babs) + item * nthr + tid, s_abs[tid]);
         }
+        if (tid == 0 && prm.unsorted != nullptr && s_unsorted) atomicOr(prm.unsorted + item, s_unsorted);
         if (tid < 32 && prm.first_pos != nullptr) {
             const int m = tid >> 4, c = tid & 15;
             if (c < K) {
@@ -789,7 +861,7 @@ static int make_label_map(CUtensorMap* tm, const uint8_t* base, long long rows, 
     return OCTM_OK;
 }
 
-template <int NP, bool CONF, bool COLS, bool SEEDS>
+template <int NP, bool CONF, bool COLS, bool SEEDS, bool SORT>
 static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     LabelPassParams p = p0;
     p.one = 1;
@@ -822,13 +894,14 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
         if (p.bsq) ok = ok && cudaMemsetAsync(p.bsq, 0, n * (k - 1) * 8, stream) == cudaSuccess;
         if (p.babs) ok = ok && cudaMemsetAsync(p.babs, 0, n * (k - 1) * 8, stream) == cudaSuccess;
         if (p.first_pos) ok = ok && cudaMemsetAsync(p.first_pos, 0xff, n * 2 * k * 4, stream) == cudaSuccess;
+        if (p.unsorted) ok = ok && cudaMemsetAsync(p.unsorted, 0, n * 4, stream) == cudaSuccess;
         if (!ok) return fail(OCTM_ERR_LAUNCH, "label pass: clearing the outputs failed");
     }
     CUtensorMap tm_true, tm_pred;
     const long long rows = p.n_items * p.H;
     if (int e = make_label_map(&tm_true, p.yt, rows, p.W, R)) return e;
     if (int e = make_label_map(&tm_pred, p.yp, rows, p.W, R)) return e;
-    auto kern = NW > 8 ? label_pass_fast<NP, CONF, COLS, SEEDS, true> : label_pass_fast<NP, CONF, COLS, SEEDS, false>;
+    auto kern = NW > 8 ? label_pass_fast<NP, CONF, COLS, SEEDS, SORT, true> : label_pass_fast<NP, CONF, COLS, SEEDS, SORT, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess)
         return fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(label_pass_fast) failed");
     const int threads = NW * 32;
@@ -843,14 +916,14 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     return check_launch("label_pass_fast");
 }
 
-template <bool CONF, bool COLS, bool SEEDS>
+template <bool CONF, bool COLS, bool SEEDS, bool SORT>
 static int dispatch_np(const LabelPassParams& p, cudaStream_t stream) {
     const int np = p.K / 2;   // ceil((K-1)/2)
     switch (np) {
-        case 1: return launch_fast<1, CONF, COLS, SEEDS>(p, stream);
-        case 2: return launch_fast<2, CONF, COLS, SEEDS>(p, stream);
-        case 3: return launch_fast<3, CONF, COLS, SEEDS>(p, stream);
-        default: return launch_fast<4, CONF, COLS, SEEDS>(p, stream);
+        case 1: return launch_fast<1, CONF, COLS, SEEDS, SORT>(p, stream);
+        case 2: return launch_fast<2, CONF, COLS, SEEDS, SORT>(p, stream);
+        case 3: return launch_fast<3, CONF, COLS, SEEDS, SORT>(p, stream);
+        default: return launch_fast<4, CONF, COLS, SEEDS, SORT>(p, stream);
     }
 }
 
@@ -868,6 +941,8 @@ static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
         if (p.first_pos) ok = ok && cudaMemsetAsync(p.first_pos, 0xff, n * 2 * k * 4, stream) == cudaSuccess;
         if (!ok) return fail(OCTM_ERR_LAUNCH, "memset of the label-pass outputs failed");
     }
+    if (p.unsorted != nullptr && cudaMemsetAsync(p.unsorted, 0, static_cast<size_t>(p.n_items) * 4, stream) != cudaSuccess)
+        return fail(OCTM_ERR_LAUNCH, "memset of the label-pass outputs failed");
     long long grid = p.n_items * strips;
     if (grid > resident) grid = resident;
     OCTM_TIMED("label_pass_generic", stream) label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p, strips);
@@ -879,11 +954,12 @@ int run_label_pass(const LabelPassParams& p, bool conf, bool cols, bool seeds, c
     if (fast_ok(p.H, p.W, p.K, p.yt, p.yp) && p.n_items * p.H < (1ll << 31) /* TMA row coordinate */ &&
         (p.bnd_t == nullptr || reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0) &&
         (p.bnd_p == nullptr || reinterpret_cast<uintptr_t>(p.bnd_p) % 16 == 0)) {
-        if (conf && cols && seeds) return dispatch_np<true, true, true>(p, stream);
-        if (conf && cols) return dispatch_np<true, true, false>(p, stream);
-        if (conf && !cols && !seeds) return dispatch_np<true, false, false>(p, stream);
-        if (!conf && cols && !seeds) return dispatch_np<false, true, false>(p, stream);
-        return dispatch_np<true, true, true>(p, stream);
+        if (p.unsorted != nullptr) return dispatch_np<true, true, true, true>(p, stream);     // the suite's call: everything
+        if (conf && cols && seeds) return dispatch_np<true, true, true, false>(p, stream);
+        if (conf && cols) return dispatch_np<true, true, false, false>(p, stream);
+        if (conf && !cols && !seeds) return dispatch_np<true, false, false, false>(p, stream);
+        if (!conf && cols && !seeds) return dispatch_np<false, true, false, false>(p, stream);
+        return dispatch_np<true, true, true, false>(p, stream);
     }
     return launch_generic(p, stream);
 }
@@ -903,6 +979,14 @@ extern "C" int octm_label_pass_u8(const uint8_t* y_true, const uint8_t* y_pred, 
                                   int num_classes, uint64_t* counts, int64_t* thick_absdiff, int64_t* bnd_sq,
                                   int64_t* bnd_abs, int32_t* bnd_true, int32_t* bnd_pred, uint32_t* first_pos,
                                   void* stream) {
+    return octm_label_pass_sorted_u8(y_true, y_pred, n_items, H, W, num_classes, counts, thick_absdiff, bnd_sq, bnd_abs,
+                                     bnd_true, bnd_pred, first_pos, nullptr, stream);
+}
+
+extern "C" int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int H, int W,
+                                         int num_classes, uint64_t* counts, int64_t* thick_absdiff, int64_t* bnd_sq,
+                                         int64_t* bnd_abs, int32_t* bnd_true, int32_t* bnd_pred, uint32_t* first_pos,
+                                         uint32_t* unsorted, void* stream) {
     if (int e = check_common(y_true, y_pred, n_items, num_classes)) return e;
     if (H < 1 || W < 1) return octm::fail(OCTM_ERR_INVALID, "H, W must be >= 1");
     if (static_cast<long long>(H) * W >= (1ll << 32)) return octm::fail(OCTM_ERR_UNSUPPORTED, "H*W >= 2^32");
@@ -913,7 +997,9 @@ extern "C" int octm_label_pass_u8(const uint8_t* y_true, const uint8_t* y_pred, 
     p.thick = reinterpret_cast<long long*>(thick_absdiff);
     p.bsq = reinterpret_cast<long long*>(bnd_sq);
     p.babs = reinterpret_cast<long long*>(bnd_abs);
-    p.bnd_t = bnd_true; p.bnd_p = bnd_pred; p.first_pos = first_pos;
+    p.bnd_t = bnd_true; p.bnd_p = bnd_pred; p.first_pos = first_pos; p.unsorted = unsorted;
+    if (unsorted != nullptr && !(counts && thick_absdiff && bnd_sq && bnd_abs && first_pos))
+        return octm::fail(OCTM_ERR_INVALID, "unsorted needs counts, the column sums and first_pos (the full pass)");
     const bool conf = counts != nullptr;
     const bool cols = thick_absdiff || bnd_sq || bnd_abs || bnd_true;
     const bool seeds = first_pos != nullptr;

@@ -63,6 +63,7 @@ class LabelPassOut:
     bnd_true: torch.Tensor | None = None        # [N, K-1, W] int32
     bnd_pred: torch.Tensor | None = None
     first_pos: torch.Tensor | None = None       # [N, 2, K]  uint32 bits
+    unsorted: torch.Tensor | None = None        # [N] bit 0 / 1: a column of y_true / y_pred is not in class order
 
 
 class _Timed:
@@ -84,8 +85,9 @@ class _Timed:
 
 
 def label_pass(y_true, y_pred, num_classes, *, counts=True, columns=True, seeds=False, boundaries=False,
-               timers=None):
-    """One read of both label tensors -> confusion matrices, column-scan sums, contour seeds."""
+               timers=None, certify=False):
+    """One read of both label tensors -> confusion matrices, column-scan sums, contour seeds; ``certify`` adds the
+    per-item layering certificate ``unsorted`` (needs counts, columns and seeds)."""
     yt, yp = _check_pair(y_true, y_pred)
     n, h, w = yt.shape
     k = int(num_classes)
@@ -103,10 +105,12 @@ def label_pass(y_true, y_pred, num_classes, *, counts=True, columns=True, seeds=
             out.bnd_pred = torch.empty((n, k - 1, w), dtype=torch.int32, device=dev)
         if seeds:
             out.first_pos = torch.empty((n, 2, k), dtype=torch.int32, device=dev)
+        if certify:
+            out.unsorted = torch.empty((n,), dtype=torch.int32, device=dev)
         with _Timed(timers, "label_pass"):
-            _lib.call("octm_label_pass_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(out.counts),
+            _lib.call("octm_label_pass_sorted_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(out.counts),
                       _ptr(out.thick_absdiff), _ptr(out.bnd_sq), _ptr(out.bnd_abs), _ptr(out.bnd_true),
-                      _ptr(out.bnd_pred), _ptr(out.first_pos), _stream())
+                      _ptr(out.bnd_pred), _ptr(out.first_pos), _ptr(out.unsorted), _stream())
     return out
 
 
@@ -249,14 +253,14 @@ def _vertex_scratch(dev, numel):
     return buf[:numel]
 
 
-def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None, bnd=None):
+def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=None, bnd=None, unsorted=None):
     n, h, w = yt.shape
     max_pts = (int(max_pts) + 3) & ~3          # vertices are stored in 16-byte groups
     dev = yt.device
     i32 = dict(dtype=torch.int32, device=dev)
     numel = (n * k * 2 * max_pts + 63) & ~63          # 256-byte multiples (octm_contour2d_metrics_u8's workspace layout)
     # stream-ordered reuse: every consumer of the scratch is enqueued on the same stream
-    scratch = None if (want_verts and want_sq) else _vertex_scratch(dev, 2 * numel)
+    scratch = None if (want_verts and want_sq) else _vertex_scratch(dev, 2 * numel + 64)
     nv = n * k * 2 * max_pts
     verts = torch.empty((n, k, 2, max_pts), **i32) if want_verts else scratch[:nv].view(n, k, 2, max_pts)
     sq = torch.empty((n, k, 2, max_pts), **i32) if want_sq else scratch[numel:numel + nv].view(n, k, 2, max_pts)
@@ -269,7 +273,7 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
         # the production path: layered pairs are measured from the boundary rows, the rest through vertex lists
         with _Timed(timers, "contour"):
             _lib.call("octm_contour2d_metrics_u8", _ptr(yt), _ptr(yp), n, h, w, k, _ptr(first_pos), _ptr(bnd[0]),
-                      _ptr(bnd[1]), max_pts, _ptr(n_pts), _ptr(flags), _ptr(max_sq), _ptr(p95), _ptr(sums),
+                      _ptr(bnd[1]), _ptr(unsorted), max_pts, _ptr(n_pts), _ptr(flags), _ptr(max_sq), _ptr(p95), _ptr(sums),
                       _ptr(scratch), scratch.numel() * 4, _stream())
         return ContourOut(n_pts, flags, max_sq, p95, sums, None, None, max_pts)
     with _Timed(timers, "contour_trace"):
@@ -283,11 +287,13 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
 
 
 def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
-                 return_sq=False, timers=None, check_overflow=True, boundaries=None):
+                 return_sq=False, timers=None, check_overflow=True, boundaries=None, unsorted=None):
     """Contour ``[0]`` of every class mask of both maps, then hausdorff / hd95 / assd integers.
 
     ``boundaries``: optional ``(bnd_true, bnd_pred)`` int32 ``[N, K-1, W]`` of the label pass; with them the
     contours of layered maps are verified and emitted in parallel instead of walked (same vertices).
+    ``unsorted``: optional layering certificate ``[N]`` of ``label_pass(certify=True)``; with it (and the boundary
+    rows) certified items are verified and measured from the boundary rows alone.
 
     Items are processed in chunks so the vertex workspace stays under ~1 GiB; items whose contour is
     longer than ``max_pts`` are re-run on their own with a larger bound."""
@@ -317,7 +323,8 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
             parts.append(_contour_chunk(yt[s:e], yp[s:e], k, first_pos[s:e], max_pts, return_vertices, return_sq, timers,
-                                        None if boundaries is None else (boundaries[0][s:e], boundaries[1][s:e])))
+                                        None if boundaries is None else (boundaries[0][s:e], boundaries[1][s:e]),
+                                        None if unsorted is None else unsorted[s:e]))
         if len(parts) == 1:
             out = parts[0]
         else:
@@ -439,6 +446,8 @@ class SuiteResult:
             d["boundary_pred"] = lp.bnd_pred.cpu().numpy()
         if lp.first_pos is not None:
             d["first_pos"] = lp.first_pos.cpu().numpy().view(np.uint32)
+        if lp.unsorted is not None:
+            d["unsorted"] = lp.unsorted.cpu().numpy().view(np.uint32)
         if ct is not None:
             d["contour_n_pts"] = ct.n_pts.cpu().numpy().view(np.uint32)
             d["contour_flags"] = ct.flags.cpu().numpy().view(np.uint32)
@@ -496,11 +505,11 @@ def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, ma
     yt, yp = _check_pair(y_true, y_pred)
     # the contour stage uses the label pass's boundary rows to skip the walk on layered maps
     lp = label_pass(yt, yp, num_classes, counts=True, columns=True, seeds=contours, boundaries=boundaries or contours,
-                    timers=timers)
+                    timers=timers, certify=contours)
     ct = None
     if contours:
         ct = contour_pass(yt, yp, num_classes, lp.first_pos, max_pts=max_pts, timers=timers, check_overflow=False,
-                          boundaries=(lp.bnd_true, lp.bnd_pred))
+                          boundaries=(lp.bnd_true, lp.bnd_pred), unsorted=lp.unsorted)
         if not boundaries:
             lp.bnd_true = lp.bnd_pred = None
     cls, bnd, tot = derive_on_device(lp, ct, yt.shape[0], timers)
@@ -516,7 +525,7 @@ def _cat_results(parts):
     lps = [p.labels for p in parts]
     lp = LabelPassOut(lps[0].num_classes, lps[0].height, lps[0].width,
                       *[cat(lps, f) for f in ("counts", "thick_absdiff", "bnd_sq", "bnd_abs", "bnd_true", "bnd_pred",
-                                              "first_pos")])
+                                              "first_pos", "unsorted")])
     ct = None
     if parts[0].contours is not None:
         cts = [p.contours for p in parts]
