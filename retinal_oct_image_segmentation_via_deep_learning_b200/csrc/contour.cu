@@ -24,6 +24,7 @@
 //                        kept as independent checks of the default path.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "trace_core.h"
@@ -252,6 +253,10 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
         const int brow = inv ? cls : cls - 1;              // h = #{label < brow + 1}
         bool ok = brow >= 0 && brow < K - 1;
         const int* hrow = (m ? prm.bnd_p : prm.bnd_t) + (item * (K - 1) + (ok ? brow : 0)) * static_cast<long long>(W);
+        // The path's raster-first pixel must be the seed (checked in full at the end): unless the seed sits exactly on
+        // the candidate in its own column there is nothing to verify -- the usual fate of a noisy prediction, whose
+        // contour [0] is the blob around a stray pixel far above the layer.
+        if (ok && hrow[seed % static_cast<uint32_t>(W)] != static_cast<int>(seed / static_cast<uint32_t>(W))) ok = false;
         uint32_t base = 0, minkey = 0xffffffffu;
         bool bad = false;
         // 64 columns per step, two adjacent columns (2 l, 2 l + 1) per lane: W is even on this path
@@ -1368,6 +1373,7 @@ __global__ void __launch_bounds__(128) distance_select_kernel(const SelectParams
 constexpr int kLdWarps = 4;           // one CTA = one (item, class) pair: the tables are shared, the query blocks dealt out
 constexpr int kLdPad = 32;            // empty columns on both sides of a table: the scan needs no clamping up to d = 32
 constexpr int kLdRing = 512;          // odd-column query ring per warp (entries)
+constexpr int kLdShort = 64;          // vertex lists up to this length are searched by brute force in the fused kernel
 #ifndef OCTM_LD_MINB
 #define OCTM_LD_MINB 10
 #endif
@@ -1385,7 +1391,8 @@ struct LayeredDistParams {
     uint32_t* max_sq;            // [n][K][2]  out; kNeedsSearch for the units left to the vertex-list search
     uint32_t* p95_sq;            // [n][K][2][2]
     double* sum_dist;            // [n][K][2]
-    uint32_t* todo_count;        // += 1 per pair left to the fallback kernels (zeroed by the host)
+    uint32_t* todo_count;        // PASS 1: += 1 per pair handed on (zeroed by the host)
+    uint32_t* search_count;      // += 1 per pair left to the vertex-list search (zeroed by the host)
 };
 
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
@@ -1434,11 +1441,208 @@ __device__ __forceinline__ void layered_nearest2(const short* lo, const short* h
     }
 }
 
-__global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_kernel(const LayeredDistParams prm) {
+// Nearest vertices of a SHORT vertex list (shared memory, {y, x} pairs) to two queries: brute force.
+__device__ __forceinline__ void list_nearest2(const int2* pts, int n, int qy0, int qx0, int qy1, int qx1, int& best0, int& best1) {
+    best0 = best1 = 0x7fffffff;
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        const int2 v = pts[i];                                   // one address for the whole warp: a broadcast
+        const int dy0 = v.x - qy0, dx0 = v.y - qx0, dy1 = v.x - qy1, dx1 = v.y - qx1;
+        best0 = min(best0, dy0 * dy0 + dx0 * dx0);
+        best1 = min(best1, dy1 * dy1 + dx1 * dx1);
+    }
+}
+
+// One side of a pair as the fused kernel sees it: a height-function table or a short vertex list.
+struct LdSide {
+    const short* lo;      // table (column 0), or null
+    const short* hi;
+    const int2* pts;      // short list, or null
+    const int* best;      // list side: squared distance of every vertex to the other side (ld_list_minima)
+    int n;                // vertices of the side
+};
+
+// Squared distance of every vertex of a short list to the other side, by the whole CTA: a far blob's search radius is
+// its distance (hundreds of columns), so each thread takes every 128th source column (or vertex) of every query and
+// the minima meet in shared memory.  best[] must hold 0x7fffffff on entry.
+template <bool SRC_TABLE>
+__device__ __forceinline__ void ld_list_minima(const int2* qpts, int nq, const LdSide& src, int ncol, int tid, int* best) {
+    for (int q = 0; q < nq; ++q) {
+        const int2 v = qpts[q];
+        int b = 0x7fffffff;
+        if (SRC_TABLE) {
+            for (int c = tid; c < ncol; c += kLdWarps * 32) {
+                const int dx = c - v.y;
+                const int dy = max3i(src.lo[c] - v.x, v.x - src.hi[c], dx & 1);
+                b = min(b, dy * dy + dx * dx);
+            }
+        } else {
+            for (int i = tid; i < src.n; i += kLdWarps * 32) {
+                const int dy = src.pts[i].x - v.x, dx = src.pts[i].y - v.y;
+                b = min(b, dy * dy + dx * dx);
+            }
+        }
+        b = __reduce_min_sync(0xffffffffu, b);
+        if ((tid & 31) == 0) atomicMin(&best[q], b);
+    }
+}
+
+template <bool SRC_TABLE>
+__device__ __forceinline__ void ld_nearest2(const LdSide& src, int qy0, int qx0, int qy1, int qx1, int ncol, int& b0, int& b1) {
+    if (SRC_TABLE) layered_nearest2(src.lo, src.hi, qy0, qx0, qy1, qx1, ncol, b0, b1);
+    else list_nearest2(src.pts, src.n, qy0, qx0, qy1, qx1, b0, b1);
+}
+
+// All vertices of `qry` against `src`; the minima are counted in `bins`.  Table queries: the column blocks are dealt
+// out to the CTA's warps (lane = column for the even-column vertices, the odd-column runs compacted through the
+// warp's ring); list queries: warp 0 takes them, two per lane.
+// What happens to a query's squared distance.  FineCounter: the usual counting (values < 2048 in 16-bit counters).
+// WideCounter adds the two roles that serve directions whose distances do not fit (a blob far from its layer, layers
+// far apart): a radix select over RECOMPUTED distances -- "coarse" counts value >> shift (and sums the square roots,
+// one per query), "window" counts, at full resolution, the values of the one coarse bin that holds the percentile's
+// order statistics and keeps the smallest value above that bin.
+struct FineCounter {
+    uint32_t* bins;
+    uint32_t run_max = 0;
+    bool run_bad = false, overflow = false;
+    __device__ __forceinline__ void add(int best, bool valid, int lane) { count_minima(best, valid, lane, bins, run_max, run_bad); }
+};
+struct WideCounter {          // PASS 2 only: one code path for the three roles, chosen at run time (CTA-uniform)
+    uint32_t* bins;
+    int mode;                 // 0 fine, 1 coarse, 2 window
+    int shift;
+    uint32_t target;
+    uint32_t run_max = 0, next_min = 0xffffffffu;
+    double sum = 0.0;
+    bool run_bad = false, overflow = false;
+    __device__ __forceinline__ void add(int best, bool valid, int lane) {
+        if (mode == 0) {
+            count_minima(best, valid, lane, bins, run_max, run_bad);
+            return;
+        }
+        const uint32_t v = static_cast<uint32_t>(best), key = v >> shift;
+        const bool in = valid && (mode == 1 || key == target);
+        // coarse: value >> shift (< kCountBins by the choice of shift); window: the even values of the target bin
+        const uint32_t idx = mode == 1 ? key : (v & ((1u << shift) - 1u)) >> 1;
+        const uint32_t peers = __match_any_sync(0xffffffffu, in ? idx : static_cast<uint32_t>(kCountBins) + lane);
+        if (in && lane == __ffs(peers) - 1) atomicAdd(&bins[idx >> 1], static_cast<uint32_t>(__popc(peers)) << ((idx & 1u) * 16));
+        if (mode == 1) {
+            if (valid) sum += sqrt(static_cast<double>(best) / 4.0);
+        } else if (valid && key > target) {
+            next_min = min(next_min, v);
+        }
+    }
+};
+
+template <bool QRY_TABLE, bool SRC_TABLE, class Counter>
+__device__ __forceinline__ void ld_direction(const LdSide& qry, const LdSide& src, int W, int ncol, int warp, int lane,
+                                             uint32_t* ring, Counter& ctr) {
+    if (!QRY_TABLE) {
+        // list queries: their minima were found once by ld_list_minima (all threads of the CTA); warp 0 counts them
+        if (warp == 0) {
+            const bool v0 = lane < qry.n, v1 = lane + 32 < qry.n;
+            ctr.add(qry.best[v0 ? lane : 0], v0, lane);
+            ctr.add(qry.best[v1 ? lane + 32 : 0], v1, lane);
+        }
+        return;
+    }
+    const short* qlo = qry.lo;
+    const short* qhi = qry.hi;
+    const int nblk = (W + 63) >> 6;
+    uint32_t head = 0, tail = 0;
+    // a query that costs (next to) nothing for idle slots: a vertex of the source itself
+    const int idle_y = SRC_TABLE ? src.lo[0] : src.pts[0].x, idle_x = SRC_TABLE ? 0 : src.pts[0].y;
+    for (int blk = warp; blk < nblk; blk += kLdWarps) {          // 64 columns: lane takes x and x + 32
+        const int xa = blk * 64 + lane, xb = xa + 32;
+        const bool va = xa < W, vb = xb < W;
+        // the even-column vertices of the two columns
+        int ba, bb;
+        ld_nearest2<SRC_TABLE>(src, va ? qlo[2 * xa] : idle_y, va ? 2 * xa : idle_x, vb ? qlo[2 * xb] : idle_y, vb ? 2 * xb : idle_x, ncol, ba, bb);
+        ctr.add(ba, va, lane);
+        ctr.add(bb, vb, lane);
+        // the runs between columns x and x + 1 join the ring
+        const bool ra = xa + 1 < W, rb = xb + 1 < W;
+        const int la = ra ? qlo[2 * xa + 1] : 32767, ha = ra ? qhi[2 * xa + 1] : -32768;
+        const int lb = rb ? qlo[2 * xb + 1] : 32767, hb = rb ? qhi[2 * xb + 1] : -32768;
+        const uint32_t lena = ha >= la ? static_cast<uint32_t>((ha - la) >> 1) + 1u : 0u;
+        const uint32_t lenb = hb >= lb ? static_cast<uint32_t>((hb - lb) >> 1) + 1u : 0u;
+        const uint32_t len = lena + lenb;
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > static_cast<uint32_t>(kLdRing - 64)) { ctr.overflow = true; break; }   // absurdly steep: general path
+        uint32_t at = tail + incl - len;
+        for (uint32_t t = 0; t < lena; ++t, ++at)
+            ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(la + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xa + 1);
+        for (uint32_t t = 0; t < lenb; ++t, ++at)
+            ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(lb + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xb + 1);
+        tail += total;
+        __syncwarp();
+        while (tail - head >= 64u) {
+            const uint32_t q0 = ring[(head + lane) & (kLdRing - 1)], q1 = ring[(head + 32 + lane) & (kLdRing - 1)];
+            head += 64u;
+            int b0, b1;
+            ld_nearest2<SRC_TABLE>(src, static_cast<int>(q0 >> 16), static_cast<int>(q0 & 0xffffu), static_cast<int>(q1 >> 16),
+                                   static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
+            ctr.add(b0, true, lane);
+            ctr.add(b1, true, lane);
+        }
+        __syncwarp();
+    }
+    if (tail != head) {
+        const uint32_t left = tail - head;
+        const bool v0 = static_cast<uint32_t>(lane) < left, v1 = static_cast<uint32_t>(lane) + 32u < left;
+        const uint32_t q0 = ring[(head + (v0 ? lane : 0)) & (kLdRing - 1)];
+        const uint32_t q1 = v1 ? ring[(head + 32 + lane) & (kLdRing - 1)] : q0;
+        int b0, b1;
+        ld_nearest2<SRC_TABLE>(src, static_cast<int>(q0 >> 16), static_cast<int>(q0 & 0xffffu), static_cast<int>(q1 >> 16),
+                               static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
+        ctr.add(b0, v0, lane);
+        ctr.add(b1, v1, lane);
+    }
+}
+
+// The vertices of a table in column order -> verts (what trace_layered_kernel<true> would have written).
+__device__ __forceinline__ void ld_emit(const short* lo, const short* hi, int ncol, int lane, uint32_t* out, uint32_t cap) {
+    uint32_t base = 0;
+    for (int c0 = 0; c0 < ncol; c0 += 32) {
+        const int c = c0 + lane;
+        const int l = c < ncol ? lo[c] : 32767, h = c < ncol ? hi[c] : -32768;
+        const uint32_t len = h >= l ? static_cast<uint32_t>((h - l) >> 1) + 1u : 0u;
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        uint32_t at = base + incl - len;
+        for (uint32_t t = 0; t < len; ++t, ++at)
+            if (at < cap) out[at] = (static_cast<uint32_t>(l + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(c);
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// PASS 1: every pair; verification from the certificate + boundary rows; pairs with two verified sides are measured,
+//         the others are handed on (n_pts: verified side = count | kLayeredBit, other side kTraceTodo; units marked).
+// PASS 2: after trace_layered_kernel<false> (verification against label pixels) and the walk have settled the
+//         kTraceTodo sides: the marked pairs again.  A side is now a table (kLayeredBit) or a vertex list; table x
+//         table, table x short list and short x short list are measured here, the rest gets its tables emitted as
+//         vertex lists and stays marked for distance_column_kernel.
+template <int PASS>
+__global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) layered_distance_kernel(const LayeredDistParams prm) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t s_vmax[2], s_bad, s_ok[2], s_minkey[2], s_cnt[2], s_seed[2];
+    __shared__ int2 s_list[2][kLdShort];
+    __shared__ int s_lbest[2][kLdShort];
+    __shared__ double s_dsum[kLdWarps];
+    __shared__ uint32_t s_next, s_tgt[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = prm.W, K = prm.K, tab = prm.tab, ncol = 2 * W - 1;
+    if (PASS == 2 && *prm.todo_count == 0) return;
     short* const tabs = reinterpret_cast<short*>(dsm);                                   // [map][lo | hi][tab]
     uint32_t* const bins2 = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(tab) * 8);   // [dir][kCountBins / 2]
     uint32_t* const ring = bins2 + kCountBins + warp * kLdRing;                          // this warp's ring
@@ -1450,15 +1654,17 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
             tabs[(2 * m + 1) * tab + j] = -32768;
         }
     }
-    const int nblk = (W + 63) >> 6;
 
     for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
+        if (PASS == 2 && prm.max_sq[pair * 2] != kNeedsSearch) continue;                 // CTA-uniform
         __syncthreads();                     // the previous pair is finished with the tables, the counters and s_*
         const long long item = pair / K;
         const int cls = static_cast<int>(pair - item * K);
         if (tid < 2) { s_vmax[tid] = 0; s_ok[tid] = 1; s_minkey[tid] = 0xffffffffu; s_cnt[tid] = 0; }
         if (tid == 2) s_bad = 0;
-        const uint32_t unsorted = prm.unsorted[item];
+        const uint32_t unsorted = PASS == 1 ? prm.unsorted[item] : 0u;
+        uint32_t n0 = 0, n1 = 0;
+        if (PASS == 2) { n0 = prm.n_pts[pair * 2]; n1 = prm.n_pts[pair * 2 + 1]; }
         __syncthreads();
         // ---- verification + tables, warps 0-1: map 0, warps 2-3: map 1.  On a map whose columns are all in class
         // order (the label pass's certificate) contour [0] of a class mask is the height function h(x) = #{label <
@@ -1467,8 +1673,11 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
         // thinner than the step) or, for the class of pixel (0, 0), on the previous one --, and (c) the raster-first
         // pixel of the path is the seed the label pass found.  All of it is arithmetic on the boundary rows: what
         // trace_layered_kernel establishes by reading label pixels, without touching the label maps.
+        // (PASS 2: the sides flagged kLayeredBit were verified before; only their tables are built.)
         {
             const int m = warp >> 1;
+            const uint32_t nm = m ? n1 : n0;
+            const bool want = PASS == 1 || (nm != kTraceTodo && (nm & kLayeredBit));
             const uint32_t* fp = prm.first_pos + (item * 2 + m) * K;
             const uint32_t myfp = lane < K ? fp[lane] : OCTM_NO_SEED;
             const int c00 = __ffs(__ballot_sync(0xffffffffu, myfp == 0u)) - 1;
@@ -1477,13 +1686,14 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
             const uint32_t seed = inv ? others : __shfl_sync(0xffffffffu, myfp, cls);
             if (lane == 0 && (warp & 1) == 0) s_seed[m] = seed;
             const int brow = inv ? cls : cls - 1;
-            if (seed != OCTM_NO_SEED && !((unsorted >> m) & 1u) && brow >= 0 && brow < K - 1) {
+            if (want && seed != OCTM_NO_SEED && !((unsorted >> m) & 1u) && brow >= 0 && brow < K - 1) {
                 const int* rows = (m ? prm.bnd_p : prm.bnd_t) + item * (K - 1) * static_cast<long long>(W);
                 const int* hrow = rows + brow * static_cast<long long>(W);
                 // the row that bounds the class on the far side of the path: the next boundary (band thickness) for a
                 // class below the path, the previous one for the class of pixel (0, 0); null = nothing to check
                 const int* orow = inv ? (cls > 0 ? rows + (cls - 1) * static_cast<long long>(W) : nullptr)
                                       : (cls < K - 1 ? rows + cls * static_cast<long long>(W) : nullptr);
+                if (PASS == 2) orow = nullptr;
                 uint32_t* lo32 = reinterpret_cast<uint32_t*>(tabs + (2 * m) * tab + kLdPad);
                 uint32_t* hi32 = lo32 + (tab >> 1);
                 bool ok = true;
@@ -1499,10 +1709,12 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
                     if (x >= W - 1) hn = h;
                     const int o = orow != nullptr ? orow[xc] : (inv ? 0 : H);
                     if (x < W) {
-                        const int lo_w = min(hl, min(h, hn)), hi_w = max(hl, max(h, hn));
-                        ok = ok && h >= 1 && h <= H - 1 && (inv ? o <= lo_w - 1 : o >= hi_w + 1);
-                        minkey = min(minkey, static_cast<uint32_t>(h) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x));
-                        steps += static_cast<uint32_t>(abs(hn - h));
+                        if (PASS == 1) {
+                            const int lo_w = min(hl, min(h, hn)), hi_w = max(hl, max(h, hn));
+                            ok = ok && h >= 1 && h <= H - 1 && (inv ? o <= lo_w - 1 : o >= hi_w + 1);
+                            minkey = min(minkey, static_cast<uint32_t>(h) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x));
+                            steps += static_cast<uint32_t>(abs(hn - h));
+                        }
                         // columns 2 x and 2 x + 1 as one 32-bit store per table (column 2 W - 1 is a pad)
                         const uint32_t e = static_cast<uint32_t>(2 * h - 1) & 0xffffu;
                         const bool run = hn != h;
@@ -1512,111 +1724,110 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
                         hi32[x] = e | (oh << 16);
                     }
                 }
-                ok = __all_sync(0xffffffffu, ok);
-                minkey = __reduce_min_sync(0xffffffffu, minkey);
-                steps = __reduce_add_sync(0xffffffffu, steps);
-                if (lane == 0) {
-                    if (!ok) s_ok[m] = 0;
-                    atomicMin(&s_minkey[m], minkey);
-                    atomicAdd(&s_cnt[m], steps);
+                if (PASS == 1) {
+                    ok = __all_sync(0xffffffffu, ok);
+                    minkey = __reduce_min_sync(0xffffffffu, minkey);
+                    steps = __reduce_add_sync(0xffffffffu, steps);
+                    if (lane == 0) {
+                        if (!ok) s_ok[m] = 0;
+                        atomicMin(&s_minkey[m], minkey);
+                        atomicAdd(&s_cnt[m], steps);
+                    }
                 }
-            } else if (lane == 0) {
+            } else if (PASS == 1 && lane == 0) {
                 s_ok[m] = 0;
+            }
+            if (PASS == 2 && !want && nm != kTraceTodo && nm != 0 && nm <= static_cast<uint32_t>(kLdShort)) {
+                // a short vertex list (a walked blob): into shared memory as {y, x}
+                const uint32_t* v = prm.verts + (pair * 2 + m) * static_cast<long long>(prm.max_pts);
+                for (int i = (warp & 1) * 32 + lane; i < static_cast<int>(nm); i += 64) {
+                    const uint32_t w = v[i];
+                    s_list[m][i] = make_int2(static_cast<int>(w >> 16), static_cast<int>(w & 0xffffu));
+                    s_lbest[m][i] = 0x7fffffff;
+                }
             }
         }
         __syncthreads();
-        // per map: 0 = no contour, count = verified height function, kTraceTodo = left to the fallback kernels
-        uint32_t n0, n1;
-        {
+        if (PASS == 1) {
+            // per map: 0 = no contour, count = verified height function, kTraceTodo = left to the fallback kernels
             const uint32_t c0 = static_cast<uint32_t>(W) + s_cnt[0], c1 = static_cast<uint32_t>(W) + s_cnt[1];
             n0 = s_seed[0] == OCTM_NO_SEED ? 0u
-                 : (s_ok[0] && s_minkey[0] == s_seed[0] && c0 <= static_cast<uint32_t>(prm.max_pts) ? c0 : kTraceTodo);
+                 : (s_ok[0] && s_minkey[0] == s_seed[0] && c0 <= static_cast<uint32_t>(prm.max_pts) ? (c0 | kLayeredBit) : kTraceTodo);
             n1 = s_seed[1] == OCTM_NO_SEED ? 0u
-                 : (s_ok[1] && s_minkey[1] == s_seed[1] && c1 <= static_cast<uint32_t>(prm.max_pts) ? c1 : kTraceTodo);
+                 : (s_ok[1] && s_minkey[1] == s_seed[1] && c1 <= static_cast<uint32_t>(prm.max_pts) ? (c1 | kLayeredBit) : kTraceTodo);
         }
-        const bool lay0 = n0 != 0 && n0 != kTraceTodo, lay1 = n1 != 0 && n1 != kTraceTodo;
-        const uint32_t cnt0 = n0, cnt1 = n1;
+        const bool todo0 = n0 == kTraceTodo, todo1 = n1 == kTraceTodo;        // PASS 2: cannot happen (the walk settles them)
+        const bool lay0 = !todo0 && (n0 & kLayeredBit), lay1 = !todo1 && (n1 & kLayeredBit);
+        const uint32_t cnt0 = todo0 ? 0u : n0 & ~kLayeredBit, cnt1 = todo1 ? 0u : n1 & ~kLayeredBit;
         if (n0 == 0 || n1 == 0) {            // a mask without a contour: nothing to measure (reference: IndexError)
-            const bool todo = n0 == kTraceTodo || n1 == kTraceTodo;       // the other side is still walked for its n_pts
+            const bool todo = todo0 || todo1;                                 // the other side is still walked for its n_pts
             if (tid < 2) {
-                prm.n_pts[pair * 2 + tid] = tid ? n1 : n0;
+                prm.n_pts[pair * 2 + tid] = tid ? (todo1 ? n1 : cnt1) : (todo0 ? n0 : cnt0);
                 prm.max_sq[pair * 2 + tid] = todo ? kNeedsSearch : 0u;
                 prm.p95_sq[pair * 4 + tid * 2] = prm.p95_sq[pair * 4 + tid * 2 + 1] = 0;
                 prm.sum_dist[pair * 2 + tid] = 0.0;
             }
-            if (todo && tid == 0) atomicAdd(prm.todo_count, 1u);
+            if (PASS == 1 && todo && tid == 0) atomicAdd(prm.todo_count, 1u);
             continue;
         }
-        bool done = lay0 && lay1;            // CTA-uniform
+        if (PASS == 1 && (todo0 || todo1)) {      // handed on: the verified side keeps its flag, nothing is emitted yet
+            if (tid < 2) {
+                prm.n_pts[pair * 2 + tid] = tid ? n1 : n0;
+                prm.max_sq[pair * 2 + tid] = kNeedsSearch;
+            }
+            if (tid == 2) atomicAdd(prm.todo_count, 1u);
+            continue;
+        }
+        const bool short0 = !lay0 && cnt0 <= static_cast<uint32_t>(kLdShort), short1 = !lay1 && cnt1 <= static_cast<uint32_t>(kLdShort);
+        bool done = (lay0 || short0) && (lay1 || short1);            // CTA-uniform
         if (done) {
-            for (int dir = 0; dir < 2; ++dir) {
-                // direction 0: queries = pred vertices (map 1), sources = true vertices (map 0); direction 1 swapped
-                const short* slo = tabs + (2 * dir) * tab + kLdPad;
-                const short* shi = slo + tab;
-                const short* qlo = tabs + (2 * (1 - dir)) * tab + kLdPad;
-                const short* qhi = qlo + tab;
-                uint32_t* bins = bins2 + dir * (kCountBins / 2);
-                uint32_t run_max = 0, head = 0, tail = 0;
-                bool run_bad = false;
-                // a query that costs nothing (its own column of the source: distance 0 at d = 0) for idle slots
-                const int idle_y = slo[0];
-                for (int blk = warp; blk < nblk; blk += kLdWarps) {          // 64 columns: lane takes x and x + 32
-                    const int xa = blk * 64 + lane, xb = xa + 32;
-                    const bool va = xa < W, vb = xb < W;
-                    // the even-column vertices of the two columns
-                    int ba, bb;
-                    layered_nearest2(slo, shi, va ? qlo[2 * xa] : idle_y, va ? 2 * xa : 0, vb ? qlo[2 * xb] : idle_y, vb ? 2 * xb : 0,
-                                     ncol, ba, bb);
-                    count_minima(ba, va, lane, bins, run_max, run_bad);
-                    count_minima(bb, vb, lane, bins, run_max, run_bad);
-                    // the runs between columns x and x + 1 join the ring
-                    const bool ra = xa + 1 < W, rb = xb + 1 < W;
-                    const int la = ra ? qlo[2 * xa + 1] : 32767, ha = ra ? qhi[2 * xa + 1] : -32768;
-                    const int lb = rb ? qlo[2 * xb + 1] : 32767, hb = rb ? qhi[2 * xb + 1] : -32768;
-                    const uint32_t lena = ha >= la ? static_cast<uint32_t>((ha - la) >> 1) + 1u : 0u;
-                    const uint32_t lenb = hb >= lb ? static_cast<uint32_t>((hb - lb) >> 1) + 1u : 0u;
-                    const uint32_t len = lena + lenb;
-                    uint32_t incl = len;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total > static_cast<uint32_t>(kLdRing - 64)) { run_bad = true; break; }   // absurdly steep: general path
-                    uint32_t at = tail + incl - len;
-                    for (uint32_t t = 0; t < lena; ++t, ++at)
-                        ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(la + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xa + 1);
-                    for (uint32_t t = 0; t < lenb; ++t, ++at)
-                        ring[at & (kLdRing - 1)] = (static_cast<uint32_t>(lb + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xb + 1);
-                    tail += total;
-                    __syncwarp();
-                    while (tail - head >= 64u) {
-                        const uint32_t q0 = ring[(head + lane) & (kLdRing - 1)], q1 = ring[(head + 32 + lane) & (kLdRing - 1)];
-                        head += 64u;
-                        int b0, b1;
-                        layered_nearest2(slo, shi, static_cast<int>(q0 >> 16), static_cast<int>(q0 & 0xffffu), static_cast<int>(q1 >> 16),
-                                         static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
-                        count_minima(b0, true, lane, bins, run_max, run_bad);
-                        count_minima(b1, true, lane, bins, run_max, run_bad);
-                    }
-                    __syncwarp();
+            LdSide sd0, sd1;
+            sd0.lo = lay0 ? tabs + kLdPad : nullptr;
+            sd0.hi = lay0 ? tabs + tab + kLdPad : nullptr;
+            sd0.pts = s_list[0];
+            sd0.best = s_lbest[0];
+            sd0.n = static_cast<int>(cnt0);
+            sd1.lo = lay1 ? tabs + 2 * tab + kLdPad : nullptr;
+            sd1.hi = lay1 ? tabs + 3 * tab + kLdPad : nullptr;
+            sd1.pts = s_list[1];
+            sd1.best = s_lbest[1];
+            sd1.n = static_cast<int>(cnt1);
+            if constexpr (PASS == 2) if (!lay0 || !lay1) {         // the short lists' own minima, once
+                if (!lay0) { if (lay1) ld_list_minima<true>(s_list[0], sd0.n, sd1, ncol, tid, s_lbest[0]); else ld_list_minima<false>(s_list[0], sd0.n, sd1, ncol, tid, s_lbest[0]); }
+                if (!lay1) { if (lay0) ld_list_minima<true>(s_list[1], sd1.n, sd0, ncol, tid, s_lbest[1]); else ld_list_minima<false>(s_list[1], sd1.n, sd0, ncol, tid, s_lbest[1]); }
+                __syncthreads();
+            }
+            // direction d (0: queries = pred vertices, sources = true vertices; 1: swapped); the kinds are CTA-uniform
+            auto run_dir = [&](int d, auto& ctr) {
+                LdSide q, sd;                        // field-wise selects: no indexed struct array (it would live in local memory)
+                q.lo = d ? sd0.lo : sd1.lo;  q.hi = d ? sd0.hi : sd1.hi;  q.pts = d ? sd0.pts : sd1.pts;
+                q.best = d ? sd0.best : sd1.best;  q.n = d ? sd0.n : sd1.n;
+                sd.lo = d ? sd1.lo : sd0.lo;  sd.hi = d ? sd1.hi : sd0.hi;  sd.pts = d ? sd1.pts : sd0.pts;
+                sd.best = d ? sd1.best : sd0.best;  sd.n = d ? sd1.n : sd0.n;
+                const bool qt = q.lo != nullptr, st = sd.lo != nullptr;
+                if constexpr (PASS == 1) ld_direction<true, true>(q, sd, W, ncol, warp, lane, ring, ctr);
+                else if (qt && st) ld_direction<true, true>(q, sd, W, ncol, warp, lane, ring, ctr);
+                else if (qt) ld_direction<true, false>(q, sd, W, ncol, warp, lane, ring, ctr);
+                else if (st) ld_direction<false, true>(q, sd, W, ncol, warp, lane, ring, ctr);
+                else ld_direction<false, false>(q, sd, W, ncol, warp, lane, ring, ctr);
+            };
+            using Counter = typename std::conditional<PASS == 1, FineCounter, WideCounter>::type;
+#pragma unroll 1
+            for (int d = 0; d < 2; ++d) {
+                Counter fc;
+                fc.bins = bins2 + d * (kCountBins / 2);
+                if constexpr (PASS == 2) fc.mode = 0;
+                run_dir(d, fc);
+                const uint32_t wmax = __reduce_max_sync(0xffffffffu, fc.run_max);
+                const bool bad = __any_sync(0xffffffffu, fc.run_bad), ovf = __any_sync(0xffffffffu, fc.overflow);
+                if (lane == 0) {
+                    atomicMax(&s_vmax[d], wmax);
+                    if (bad || ovf) atomicOr(&s_bad, (bad ? 1u << d : 0u) | (ovf ? 4u : 0u));
                 }
-                if (tail != head) {
-                    const uint32_t left = tail - head;
-                    const bool v0 = static_cast<uint32_t>(lane) < left, v1 = static_cast<uint32_t>(lane) + 32u < left;
-                    const uint32_t q0 = ring[(head + (v0 ? lane : 0)) & (kLdRing - 1)];
-                    const uint32_t q1 = v1 ? ring[(head + 32 + lane) & (kLdRing - 1)] : q0;
-                    int b0, b1;
-                    layered_nearest2(slo, shi, static_cast<int>(q0 >> 16), static_cast<int>(q0 & 0xffffu), static_cast<int>(q1 >> 16),
-                                     static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
-                    count_minima(b0, v0, lane, bins, run_max, run_bad);
-                    count_minima(b1, v1, lane, bins, run_max, run_bad);
-                }
-                publish_counts(run_max, run_bad, lane, &s_vmax[dir], &s_bad);
             }
             __syncthreads();                 // both directions counted
-            done = s_bad == 0;
+            const uint32_t badbits = s_bad;
+            done = badbits == 0;
             if (done) {
                 if (warp < 2)
                     stats_from_counters(bins2 + warp * (kCountBins / 2), s_vmax[warp], static_cast<int>(warp ? cnt0 : cnt1), lane,
@@ -1624,37 +1835,132 @@ __global__ void __launch_bounds__(kLdWarps * 32, OCTM_LD_MINB) layered_distance_
                 if (tid >= 64 && tid < 66) prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
                 continue;
             }
-            for (int i = tid; i < kCountBins; i += kLdWarps * 32) bins2[i] = 0;      // a value the counters cannot hold
-        }
-        // ---- left to the vertex-list search: emit the verified sides' vertices in column order (warp m: map m)
-        if (warp < 2 && (warp ? lay1 : lay0)) {
-            const int m = warp;
-            const short* lo = tabs + (2 * m) * tab + kLdPad;
-            const short* hi = lo + tab;
-            uint32_t* out = prm.verts + (pair * 2 + m) * static_cast<long long>(prm.max_pts);
-            uint32_t base = 0;
-            for (int c0 = 0; c0 < ncol; c0 += 32) {
-                const int c = c0 + lane;
-                const int l = c < ncol ? lo[c] : 32767, h = c < ncol ? hi[c] : -32768;
-                const uint32_t len = h >= l ? static_cast<uint32_t>((h - l) >> 1) + 1u : 0u;
-                uint32_t incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += up;
+            if constexpr (PASS == 1) if (!(badbits & 4u)) {
+                // distances the counters cannot hold: PASS 2 measures the pair again with the wide counting below
+                for (int i = tid; i < kCountBins; i += kLdWarps * 32) bins2[i] = 0;
+                if (tid < 2) {
+                    prm.n_pts[pair * 2 + tid] = tid ? n1 : n0;
+                    prm.max_sq[pair * 2 + tid] = kNeedsSearch;
                 }
-                uint32_t at = base + incl - len;
-                for (uint32_t t = 0; t < len; ++t, ++at)
-                    if (at < static_cast<uint32_t>(prm.max_pts))
-                        out[at] = (static_cast<uint32_t>(l + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(c);
-                base += __shfl_sync(0xffffffffu, incl, 31);
+                if (tid == 2) atomicAdd(prm.todo_count, 1u);
+                continue;
             }
-            if (lane == 0) prm.n_pts[pair * 2 + m] = m ? cnt1 : cnt0;
-        } else if (warp < 2 && lane == 0) {
-            prm.n_pts[pair * 2 + warp] = kTraceTodo;
+            if constexpr (PASS == 2) if (!(badbits & 4u) && max(s_vmax[0], s_vmax[1]) < (static_cast<uint32_t>(kCountBins) << 11)) {
+                // ---- wide counting: per direction either the usual statistics, or a two-level radix select over
+                // recomputed distances (coarse bins of 2^shift values; then the bin of the percentile at full resolution)
+#pragma unroll 1
+                for (int d = 0; d < 2; ++d) {
+                    uint32_t* bins = bins2 + d * (kCountBins / 2);
+                    const int nq = static_cast<int>(d ? cnt0 : cnt1);
+                    if (!((badbits >> d) & 1u)) {
+                        if (warp == 0)
+                            stats_from_counters(bins, s_vmax[d], nq, lane, prm.max_sq + pair * 2 + d, prm.p95_sq + (pair * 2 + d) * 2,
+                                                prm.sum_dist + pair * 2 + d);
+                        continue;                        // CTA-uniform
+                    }
+                    const uint32_t vmax = s_vmax[d];
+                    int shift = 1;
+                    while ((vmax >> shift) >= static_cast<uint32_t>(kCountBins)) ++shift;        // <= 11 by the guard above
+                    __syncthreads();
+                    for (int i = tid; i < kCountBins / 2; i += kLdWarps * 32) bins[i] = 0;
+                    if (tid < kLdWarps) s_dsum[tid] = 0.0;
+                    if (tid == 0) s_next = 0xffffffffu;
+                    __syncthreads();
+                    WideCounter cc;
+                    cc.bins = bins;
+                    cc.mode = 1;
+                    cc.shift = shift;
+                    cc.target = 0;
+                    run_dir(d, cc);
+                    double ws = cc.sum;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ws = __dadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, o));
+                    if (lane == 0) s_dsum[warp] = ws;
+                    __syncthreads();
+                    // warp 0: the coarse bin of rank lo (numpy's linear percentile: lo = floor(0.95 (nq - 1)), hi = lo + 1)
+                    const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);
+                    const uint32_t lo_rank = static_cast<uint32_t>(floor(pos));
+                    const uint32_t hi_rank = lo_rank + 1 < static_cast<uint32_t>(nq) ? lo_rank + 1 : lo_rank;
+                    if (warp == 0) {
+                        uint32_t base = 0, tgt = 0, before = 0, inbin = 0;
+                        for (uint32_t h0 = 0; h0 <= (vmax >> shift); h0 += 32) {
+                            const uint32_t h = h0 + lane;
+                            const uint32_t c = (bins[h >> 1] >> ((h & 1u) * 16)) & 0xffffu;
+                            uint32_t incl = c;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += up;
+                            }
+                            const uint32_t first = base + incl - c;
+                            const uint32_t hit = __ballot_sync(0xffffffffu, c != 0 && first <= lo_rank && lo_rank < first + c);
+                            if (hit) {
+                                const int src_lane = __ffs(hit) - 1;
+                                tgt = h0 + src_lane;
+                                before = __shfl_sync(0xffffffffu, first, src_lane);
+                                inbin = __shfl_sync(0xffffffffu, c, src_lane);
+                            }
+                            base += __shfl_sync(0xffffffffu, incl, 31);
+                        }
+                        if (lane == 0) { s_tgt[0] = tgt; s_tgt[1] = before; s_tgt[2] = inbin; }
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < kCountBins / 2; i += kLdWarps * 32) bins[i] = 0;
+                    __syncthreads();
+                    WideCounter wc;
+                    wc.bins = bins;
+                    wc.mode = 2;
+                    wc.shift = shift;
+                    wc.target = s_tgt[0];
+                    run_dir(d, wc);
+                    const uint32_t wn = __reduce_min_sync(0xffffffffu, wc.next_min);
+                    if (lane == 0) atomicMin(&s_next, wn);
+                    __syncthreads();
+                    if (warp == 0) {
+                        const uint32_t r_lo = lo_rank - s_tgt[1], r_hi = hi_rank - s_tgt[1], inbin = s_tgt[2];
+                        uint32_t v_lo = 0, v_hi = 0, base = 0;
+                        const uint32_t nfine = 1u << (shift - 1);
+                        for (uint32_t h0 = 0; h0 < nfine; h0 += 32) {
+                            const uint32_t h = h0 + lane;
+                            const uint32_t c = (bins[h >> 1] >> ((h & 1u) * 16)) & 0xffffu;
+                            uint32_t incl = c;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += up;
+                            }
+                            const uint32_t first = base + incl - c;
+                            const uint32_t m_lo = __ballot_sync(0xffffffffu, c != 0 && first <= r_lo && r_lo < first + c);
+                            const uint32_t m_hi = __ballot_sync(0xffffffffu, c != 0 && first <= r_hi && r_hi < first + c);
+                            if (m_lo) v_lo = (s_tgt[0] << shift) + 2 * (h0 + __ffs(m_lo) - 1);
+                            if (m_hi) v_hi = (s_tgt[0] << shift) + 2 * (h0 + __ffs(m_hi) - 1);
+                            base += __shfl_sync(0xffffffffu, incl, 31);
+                        }
+                        if (r_hi >= inbin) v_hi = s_next;            // the next order statistic lies in a higher coarse bin
+                        if (lane == 0) {
+                            prm.max_sq[pair * 2 + d] = vmax;
+                            prm.p95_sq[(pair * 2 + d) * 2] = v_lo;
+                            prm.p95_sq[(pair * 2 + d) * 2 + 1] = v_hi;
+                            prm.sum_dist[pair * 2 + d] = __dadd_rn(__dadd_rn(s_dsum[0], s_dsum[1]), __dadd_rn(s_dsum[2], s_dsum[3]));
+                        }
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < kCountBins / 2; i += kLdWarps * 32) bins[i] = 0;
+                }
+                if (tid >= 64 && tid < 66) prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
+                continue;
+            }
+            for (int i = tid; i < kCountBins; i += kLdWarps * 32) bins2[i] = 0;      // left to the vertex-list search
         }
-        if (tid >= 64 && tid < 66) prm.max_sq[pair * 2 + (tid - 64)] = kNeedsSearch;
-        if (tid == 66) atomicAdd(prm.todo_count, 1u);
+        // ---- left to the vertex-list search: the tables become vertex lists in column order (warp m: map m)
+        if (warp < 2 && (warp ? lay1 : lay0))
+            ld_emit(tabs + (2 * warp) * tab + kLdPad, tabs + (2 * warp + 1) * tab + kLdPad, ncol, lane,
+                    prm.verts + (pair * 2 + warp) * static_cast<long long>(prm.max_pts), static_cast<uint32_t>(prm.max_pts));
+        if (tid >= 64 && tid < 66) {
+            prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
+            prm.max_sq[pair * 2 + (tid - 64)] = kNeedsSearch;
+        }
+        if (tid == 66) atomicAdd(prm.search_count, 1u);
     }
 }
 
@@ -1867,33 +2173,41 @@ extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y
         return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, false, nullptr, stream);
     }
     if (cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n_items * num_classes, s) != cudaSuccess ||
-        cudaMemsetAsync(todo, 0, sizeof(uint32_t), s) != cudaSuccess)
+        cudaMemsetAsync(todo, 0, 2 * sizeof(uint32_t), s) != cudaSuccess)
         return octm::fail(OCTM_ERR_LAUNCH, "memset(flags) failed");
-    {   // every pair: boundary-row verification, and the distances of the pairs with two verified sides
-        if (cudaFuncSetAttribute(octm::layered_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)) != cudaSuccess)
+    uint32_t* search = todo + 1;
+    const long long n_pairs = n_items * num_classes;
+    octm::LayeredDistParams lp{first_pos, bnd_true, bnd_pred, unsorted, n_pairs, H, W, num_classes, max_pts, tab, verts,
+                               n_pts, max_sq, p95_sq, sum_dist, todo, search};
+    auto launch_fused = [&](int pass) -> int {
+        auto kern = pass == 1 ? octm::layered_distance_kernel<1> : octm::layered_distance_kernel<2>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(layered_distance_kernel) failed");
         int fit = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, octm::layered_distance_kernel, octm::kLdWarps * 32, smem) != cudaSuccess || fit < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, kern, octm::kLdWarps * 32, smem) != cudaSuccess || fit < 1) {
             cudaGetLastError();
             fit = 1;
         }
-        const long long n_pairs = n_items * num_classes;
         long long grid = n_pairs;
         const long long cap = static_cast<long long>(octm::sm_count()) * fit;
         if (grid > cap) grid = cap;
-        octm::LayeredDistParams lp{first_pos, bnd_true, bnd_pred, unsorted, n_pairs, H, W, num_classes, max_pts, tab, verts,
-                                   n_pts, max_sq, p95_sq, sum_dist, todo};
-        OCTM_TIMED("layered_distance_kernel", s) octm::layered_distance_kernel<<<static_cast<unsigned>(grid), octm::kLdWarps * 32, smem, s>>>(lp);
-        if (int e = octm::check_launch("layered_distance_kernel")) return e;
-    }
-    // what is left (n_pts == kTraceTodo; nothing on clean layered data: the three kernels then return at once):
-    // verification against the label pixels, the walk, the vertex-list search
+        OCTM_TIMED(pass == 1 ? "layered_distance_kernel" : "layered_distance_kernel_pass2", s)
+            kern<<<static_cast<unsigned>(grid), octm::kLdWarps * 32, smem, s>>>(lp);
+        return octm::check_launch("layered_distance_kernel");
+    };
+    // 1. every pair: verification from the certificate and the boundary rows; pairs with two verified sides are measured
+    if (int e = launch_fused(1)) return e;
+    // What is handed on (nothing on clean layered data: the kernels below then return at once):
+    // 2. verification of the remaining contours against the label pixels (-> tables) ...
     octm::TraceParams p{y_true, y_pred, n_items, H, W, num_classes, max_pts, first_pos, verts, n_pts, flags,
                         bnd_true, bnd_pred, true, todo};
-    if (int e = launch_layered_trace<true>(p, s)) return e;
+    if (int e = launch_layered_trace<false>(p, s)) return e;
+    // 3. ... the walk for what is not a height function (-> vertex lists) ...
     if (int e = launch_walk(p, s)) return e;
-    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, true, todo, stream);
+    // 4. ... the handed-on pairs again: tables and short vertex lists are measured in shared memory ...
+    if (int e = launch_fused(2)) return e;
+    // 5. ... and the vertex-list search for the rest (long lists on both sides, or against a long list)
+    return run_distance(verts, n_pts, n_items, num_classes, max_pts, H, W, max_sq, p95_sq, sum_dist, d2, 0, true, search, stream);
 }
 
 extern "C" size_t octm_contour2d_workspace_bytes(int64_t n_items, int H, int W, int num_classes, int max_pts) {

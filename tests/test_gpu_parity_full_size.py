@@ -107,6 +107,30 @@ def test_cfg4_full_size_thin_and_touching_layers(cuda):
     _check_vertices_with_boundaries(yt, yp, 8, cuda, max_pts=8192)
 
 
+def test_layers_and_blobs_far_apart(cuda):
+    """Squared distances beyond what the 16-bit counters hold (>= 2048): layers displaced by tens of pixels (table x
+    table), a blob far above its layer (table x short list), two far blobs (short x short): the radix select over
+    recomputed distances in the fused kernel's second pass."""
+    k, h, w = 6, 496, 512
+    yt, _ = synth.layered_pair(4, h, w, k, seed=71)
+    yp = yt.copy()
+    yp[0] = np.roll(yt[0], 37, axis=0)                       # every boundary 37 rows lower (rows wrap into class k-1 ... 0)
+    yp[0, :37] = 0
+    yp[1] = np.roll(yt[1], -29, axis=0)
+    yp[1, -29:] = k - 1
+    yp[2, 3, 400] = 4                                        # one stray pixel of class 4 far above its layer: contour [0] = that pixel
+    yp[3, 5, 17] = 3
+    yt[3, 480, 500] = 1                                      # ... and a stray pixel below in y_true as well (not a seed: the layer comes first)
+    n = _check_suite_vs_oracle(yt, yp, k, cuda)
+    assert n == 4 * k
+    yt2 = np.zeros((2, 64, 128), np.uint8)                   # two single-pixel blobs 100+ columns apart
+    yp2 = np.zeros((2, 64, 128), np.uint8)
+    yt2[:, 5, 3] = 1
+    yp2[:, 60, 120] = 1
+    yt2[1, 30:34, 60:70] = 1
+    _check_suite_vs_oracle(yt2, yp2, 2, cuda)
+
+
 def test_cfg4_uniform_random_labels(cuda):
     """SURVEY 8d adversarial variant: every pixel a random class (worst case for the histogram and the walk)."""
     yt, yp = synth.random_pair(1, 496, 512, 8, seed=66)
