@@ -48,6 +48,7 @@ struct TraceParams {
 
 constexpr uint32_t kTraceTodo = 0xffffffffu;
 constexpr uint32_t kLayeredBit = 0x80000000u;    // n_pts: contour verified as a height function, vertices not emitted
+constexpr uint32_t kRowBit = 0x40000000u;        // n_pts (with kLayeredBit): the height row h(x) is in the contour's verts slot (int32 [W])
 constexpr uint32_t kNeedsSearch = 0xfffffffeu;   // max_sq: unit left to the general (vertex-list) distance search
 
 // Both row caches of the walk in one go: 16 aligned label bytes for the even-row cache and 16 for the odd-row
@@ -256,7 +257,21 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
         // The path's raster-first pixel must be the seed (checked in full at the end): unless the seed sits exactly on
         // the candidate in its own column there is nothing to verify -- the usual fate of a noisy prediction, whose
         // contour [0] is the blob around a stray pixel far above the layer.
-        if (ok && hrow[seed % static_cast<uint32_t>(W)] != static_cast<int>(seed / static_cast<uint32_t>(W))) ok = false;
+        // The boundary rows are COUNTS (#{label < k} per column): a stray pixel elsewhere in a column moves the count by
+        // one without touching the path.  The estimate is therefore re-centred on the step actually present in rows
+        // h - 2 .. h + 1 of the column; the window check below then validates the re-centred candidate like any other.
+        auto refine = [&](int h, int col) -> int {
+            if (h < 2 || h > H - 2) return h;
+            const uint8_t* p = L + static_cast<uint32_t>((h - 2) * W + col);
+            uint32_t pat = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) pat |= ((__ldg(p + r * W) == cls) != inv ? 1u : 0u) << r;
+            return pat == 14u ? h - 1 : (pat == 8u ? h + 1 : h);       // 0111 / 0001 / (0011 or anything else)
+        };
+        if (ok) {
+            const int xs = static_cast<int>(seed % static_cast<uint32_t>(W));
+            if (refine(hrow[xs], xs) != static_cast<int>(seed / static_cast<uint32_t>(W))) ok = false;
+        }
         uint32_t base = 0, minkey = 0xffffffffu;
         bool bad = false;
         // 64 columns per step, two adjacent columns (2 l, 2 l + 1) per lane: W is even on this path
@@ -268,14 +283,16 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
             const int x = x0 + 2 * lane;                   // this lane's first column
             const bool valid = x < W;
             const int xc = min(x, W - 2);
-            const int ha = hcur.x, hb = hcur.y;
+            const int ha = refine(hcur.x, xc), hb = refine(hcur.y, xc + 1);
             hcur = hrow2[min((x0 >> 1) + 32 + lane, W2 - 1)];      // next block's heights, in flight during the checks
             int hl = __shfl_up_sync(0xffffffffu, hb, 1);
             if (lane == 0) hl = x0 > 0 ? hleft : ha;
             int hr = __shfl_down_sync(0xffffffffu, ha, 1);
             const int hfirst_next = __shfl_sync(0xffffffffu, hcur.x, 0);
-            if (lane == 31) hr = hfirst_next;
+            if (lane == 31 && x + 2 < W) hr = refine(hfirst_next, x + 2);
             if (x + 2 >= W) hr = hb;
+            // the re-centred row is what layered_distance_kernel<2> builds this side's table from
+            if (!EMIT && valid && static_cast<uint32_t>(W) <= cap) reinterpret_cast<int2*>(out)[x >> 1] = make_int2(ha, hb);
             hleft = __shfl_sync(0xffffffffu, hb, 31);
             // all heights inside [1, H - 1] before any pixel is addressed through them (the right neighbour of
             // lane 31 belongs to the next block and has not been looked at yet)
@@ -334,7 +351,8 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
             }
         }
         if (ok) ok = !__any_sync(0xffffffffu, bad) && __reduce_min_sync(0xffffffffu, minkey) == seed;
-        if (lane == 0) *np = ok ? (EMIT ? base : (base | kLayeredBit)) : kTraceTodo;
+        if (ok && !EMIT && static_cast<uint32_t>(W) > cap) ok = false;      // no room for the row: walk it
+        if (lane == 0) *np = ok ? (EMIT ? base : (base | kLayeredBit | kRowBit)) : kTraceTodo;
     }
 }
 
@@ -1521,6 +1539,7 @@ struct WideCounter {          // PASS 2 only: one code path for the three roles,
             return;
         }
         const uint32_t v = static_cast<uint32_t>(best), key = v >> shift;
+        if (valid) run_max = max(run_max, v);
         const bool in = valid && (mode == 1 || key == target);
         // coarse: value >> shift (< kCountBins by the choice of shift); window: the even values of the target bin
         const uint32_t idx = mode == 1 ? key : (v & ((1u << shift) - 1u)) >> 1;
@@ -1606,6 +1625,40 @@ __device__ __forceinline__ void ld_direction(const LdSide& qry, const LdSide& sr
     }
 }
 
+// Statistics of the (at most 64) minima of a short list, by one warp, without counters: maximum, the two order
+// statistics of numpy's linear 95th percentile (by rank counting) and the sum of sqrt(D2 / 4) in a fixed order.
+__device__ __forceinline__ void ld_list_stats(const int* best, int n, int lane, uint32_t* max_sq, uint32_t* p95_sq, double* sum_dist) {
+    const bool v0 = lane < n, v1 = lane + 32 < n;
+    const uint32_t a = v0 ? static_cast<uint32_t>(best[lane]) : 0u, b = v1 ? static_cast<uint32_t>(best[lane + 32]) : 0u;
+    uint32_t ra = 0, rb = 0;                  // rank = values below + equal values with a smaller index
+    for (int i = 0; i < n; ++i) {
+        const uint32_t w = static_cast<uint32_t>(best[i]);
+        ra += (w < a || (w == a && i < lane)) ? 1u : 0u;
+        rb += (w < b || (w == b && i < lane + 32)) ? 1u : 0u;
+    }
+    const double pos = __dmul_rn(static_cast<double>(n - 1), 0.95);
+    const uint32_t lo = static_cast<uint32_t>(floor(pos)), hi = lo + 1 < static_cast<uint32_t>(n) ? lo + 1 : lo;
+    uint32_t v_lo = 0, v_hi = 0;
+    uint32_t m = __ballot_sync(0xffffffffu, v0 && ra == lo);
+    if (m) v_lo = __shfl_sync(0xffffffffu, a, __ffs(m) - 1);
+    m = __ballot_sync(0xffffffffu, v1 && rb == lo);
+    if (m) v_lo = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+    m = __ballot_sync(0xffffffffu, v0 && ra == hi);
+    if (m) v_hi = __shfl_sync(0xffffffffu, a, __ffs(m) - 1);
+    m = __ballot_sync(0xffffffffu, v1 && rb == hi);
+    if (m) v_hi = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+    const uint32_t vmax = __reduce_max_sync(0xffffffffu, max(a, b));
+    double ds = __dadd_rn(v0 ? sqrt(static_cast<double>(a) / 4.0) : 0.0, v1 ? sqrt(static_cast<double>(b) / 4.0) : 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ds = __dadd_rn(ds, __shfl_xor_sync(0xffffffffu, ds, o));
+    if (lane == 0) {
+        *max_sq = vmax;
+        p95_sq[0] = v_lo;
+        p95_sq[1] = v_hi;
+        *sum_dist = ds;
+    }
+}
+
 // The vertices of a table in column order -> verts (what trace_layered_kernel<true> would have written).
 __device__ __forceinline__ void ld_emit(const short* lo, const short* hi, int ncol, int lane, uint32_t* out, uint32_t cap) {
     uint32_t base = 0;
@@ -1639,7 +1692,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
     __shared__ int2 s_list[2][kLdShort];
     __shared__ int s_lbest[2][kLdShort];
     __shared__ double s_dsum[kLdWarps];
-    __shared__ uint32_t s_next, s_tgt[3];
+    __shared__ uint32_t s_next, s_tgt[3], s_amax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = prm.W, K = prm.K, tab = prm.tab, ncol = 2 * W - 1;
     if (PASS == 2 && *prm.todo_count == 0) return;
@@ -1689,6 +1742,8 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
             if (want && seed != OCTM_NO_SEED && !((unsorted >> m) & 1u) && brow >= 0 && brow < K - 1) {
                 const int* rows = (m ? prm.bnd_p : prm.bnd_t) + item * (K - 1) * static_cast<long long>(W);
                 const int* hrow = rows + brow * static_cast<long long>(W);
+                if (PASS == 2 && (nm & kRowBit))      // verified against the label pixels with a re-centred row
+                    hrow = reinterpret_cast<const int*>(prm.verts + (pair * 2 + m) * static_cast<long long>(prm.max_pts));
                 // the row that bounds the class on the far side of the path: the next boundary (band thickness) for a
                 // class below the path, the previous one for the class of pixel (0, 0); null = nothing to check
                 const int* orow = inv ? (cls > 0 ? rows + (cls - 1) * static_cast<long long>(W) : nullptr)
@@ -1758,7 +1813,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
         }
         const bool todo0 = n0 == kTraceTodo, todo1 = n1 == kTraceTodo;        // PASS 2: cannot happen (the walk settles them)
         const bool lay0 = !todo0 && (n0 & kLayeredBit), lay1 = !todo1 && (n1 & kLayeredBit);
-        const uint32_t cnt0 = todo0 ? 0u : n0 & ~kLayeredBit, cnt1 = todo1 ? 0u : n1 & ~kLayeredBit;
+        const uint32_t cnt0 = todo0 ? 0u : n0 & ~(kLayeredBit | kRowBit), cnt1 = todo1 ? 0u : n1 & ~(kLayeredBit | kRowBit);
         if (n0 == 0 || n1 == 0) {            // a mask without a contour: nothing to measure (reference: IndexError)
             const bool todo = todo0 || todo1;                                 // the other side is still walked for its n_pts
             if (tid < 2) {
@@ -1782,6 +1837,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
         bool done = (lay0 || short0) && (lay1 || short1);            // CTA-uniform
         if (done) {
             LdSide sd0, sd1;
+            bool far_hint = false;           // CTA-uniform
             sd0.lo = lay0 ? tabs + kLdPad : nullptr;
             sd0.hi = lay0 ? tabs + tab + kLdPad : nullptr;
             sd0.pts = s_list[0];
@@ -1796,6 +1852,12 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                 if (!lay0) { if (lay1) ld_list_minima<true>(s_list[0], sd0.n, sd1, ncol, tid, s_lbest[0]); else ld_list_minima<false>(s_list[0], sd0.n, sd1, ncol, tid, s_lbest[0]); }
                 if (!lay1) { if (lay0) ld_list_minima<true>(s_list[1], sd1.n, sd0, ncol, tid, s_lbest[1]); else ld_list_minima<false>(s_list[1], sd1.n, sd0, ncol, tid, s_lbest[1]); }
                 __syncthreads();
+                // a blob far from the other side (the usual fate of a stray pixel): its distances will not fit the fine
+                // counters in either direction, so the fine attempt is skipped
+                bool f = false;
+                if (!lay0 && tid < sd0.n) f = s_lbest[0][tid] >= 2 * kCountBins;
+                if (!lay1 && tid < sd1.n) f = f || s_lbest[1][tid] >= 2 * kCountBins;
+                far_hint = __syncthreads_or(f) != 0;
             }
             // direction d (0: queries = pred vertices, sources = true vertices; 1: swapped); the kinds are CTA-uniform
             auto run_dir = [&](int d, auto& ctr) {
@@ -1812,11 +1874,24 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                 else ld_direction<false, false>(q, sd, W, ncol, warp, lane, ring, ctr);
             };
             using Counter = typename std::conditional<PASS == 1, FineCounter, WideCounter>::type;
+            // PASS 2: a direction whose QUERIES are a short list is settled at once from the list's minima (warp 0)
+            const bool direct0 = PASS == 2 && !lay1, direct1 = PASS == 2 && !lay0;      // direction d: queries = side 1 - d
+            if (PASS == 2 && warp == 0) {
+                if (direct0) ld_list_stats(s_lbest[1], sd1.n, lane, prm.max_sq + pair * 2, prm.p95_sq + pair * 4, prm.sum_dist + pair * 2);
+                if (direct1) ld_list_stats(s_lbest[0], sd0.n, lane, prm.max_sq + pair * 2 + 1, prm.p95_sq + pair * 4 + 2, prm.sum_dist + pair * 2 + 1);
+            }
 #pragma unroll 1
             for (int d = 0; d < 2; ++d) {
+                if (d ? direct1 : direct0) continue;
                 Counter fc;
                 fc.bins = bins2 + d * (kCountBins / 2);
-                if constexpr (PASS == 2) fc.mode = 0;
+                if constexpr (PASS == 2) {
+                    fc.mode = 0;
+                    if (far_hint) {                  // straight to the wide counting, with the image diagonal as the bound
+                        if (tid == 0) { atomicOr(&s_bad, 1u << d); s_vmax[d] = static_cast<uint32_t>(4 * (prm.H * prm.H + W * W)); }
+                        continue;
+                    }
+                }
                 run_dir(d, fc);
                 const uint32_t wmax = __reduce_max_sync(0xffffffffu, fc.run_max);
                 const bool bad = __any_sync(0xffffffffu, fc.run_bad), ovf = __any_sync(0xffffffffu, fc.overflow);
@@ -1829,7 +1904,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
             const uint32_t badbits = s_bad;
             done = badbits == 0;
             if (done) {
-                if (warp < 2)
+                if (warp < 2 && !(warp ? direct1 : direct0))
                     stats_from_counters(bins2 + warp * (kCountBins / 2), s_vmax[warp], static_cast<int>(warp ? cnt0 : cnt1), lane,
                                         prm.max_sq + pair * 2 + warp, prm.p95_sq + (pair * 2 + warp) * 2, prm.sum_dist + pair * 2 + warp);
                 if (tid >= 64 && tid < 66) prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
@@ -1845,13 +1920,14 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                 if (tid == 2) atomicAdd(prm.todo_count, 1u);
                 continue;
             }
-            if constexpr (PASS == 2) if (!(badbits & 4u) && max(s_vmax[0], s_vmax[1]) < (static_cast<uint32_t>(kCountBins) << 11)) {
+            if constexpr (PASS == 2) if (!(badbits & 4u) && max(direct0 ? 0u : s_vmax[0], direct1 ? 0u : s_vmax[1]) < (static_cast<uint32_t>(kCountBins) << 11)) {
                 // ---- wide counting: per direction either the usual statistics, or a two-level radix select over
                 // recomputed distances (coarse bins of 2^shift values; then the bin of the percentile at full resolution)
 #pragma unroll 1
                 for (int d = 0; d < 2; ++d) {
                     uint32_t* bins = bins2 + d * (kCountBins / 2);
                     const int nq = static_cast<int>(d ? cnt0 : cnt1);
+                    if (d ? direct1 : direct0) continue;
                     if (!((badbits >> d) & 1u)) {
                         if (warp == 0)
                             stats_from_counters(bins, s_vmax[d], nq, lane, prm.max_sq + pair * 2 + d, prm.p95_sq + (pair * 2 + d) * 2,
@@ -1864,7 +1940,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     __syncthreads();
                     for (int i = tid; i < kCountBins / 2; i += kLdWarps * 32) bins[i] = 0;
                     if (tid < kLdWarps) s_dsum[tid] = 0.0;
-                    if (tid == 0) s_next = 0xffffffffu;
+                    if (tid == 0) { s_next = 0xffffffffu; s_amax = 0; }
                     __syncthreads();
                     WideCounter cc;
                     cc.bins = bins;
@@ -1872,6 +1948,10 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     cc.shift = shift;
                     cc.target = 0;
                     run_dir(d, cc);
+                    {
+                        const uint32_t wm = __reduce_max_sync(0xffffffffu, cc.run_max);
+                        if (lane == 0) atomicMax(&s_amax, wm);
+                    }
                     double ws = cc.sum;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) ws = __dadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, o));
@@ -1883,7 +1963,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     const uint32_t hi_rank = lo_rank + 1 < static_cast<uint32_t>(nq) ? lo_rank + 1 : lo_rank;
                     if (warp == 0) {
                         uint32_t base = 0, tgt = 0, before = 0, inbin = 0;
-                        for (uint32_t h0 = 0; h0 <= (vmax >> shift); h0 += 32) {
+                        for (uint32_t h0 = 0; h0 <= (s_amax >> shift); h0 += 32) {
                             const uint32_t h = h0 + lane;
                             const uint32_t c = (bins[h >> 1] >> ((h & 1u) * 16)) & 0xffffu;
                             uint32_t incl = c;
@@ -1938,7 +2018,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                         }
                         if (r_hi >= inbin) v_hi = s_next;            // the next order statistic lies in a higher coarse bin
                         if (lane == 0) {
-                            prm.max_sq[pair * 2 + d] = vmax;
+                            prm.max_sq[pair * 2 + d] = s_amax;
                             prm.p95_sq[(pair * 2 + d) * 2] = v_lo;
                             prm.p95_sq[(pair * 2 + d) * 2 + 1] = v_hi;
                             prm.sum_dist[pair * 2 + d] = __dadd_rn(__dadd_rn(s_dsum[0], s_dsum[1]), __dadd_rn(s_dsum[2], s_dsum[3]));
