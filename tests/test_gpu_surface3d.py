@@ -74,3 +74,33 @@ def test_unit_ranges_add_up(cuda):
     b = suite.surface_distance_3d(torch.from_numpy(vt).to(cuda), torch.from_numpy(vp).to(cuda), 4, units=(3, 8))
     for key in full:
         assert torch.equal(a[key] + b[key], full[key]), key
+
+
+def test_near_field_path_and_its_overflow(cuda):
+    """D2 % 16 == 0 takes the capped windowed transform (exact below (R+1)^2 = 121); a unit with a single query voxel at
+    or beyond the cap must be redone by the general kernels, while the other units of the same call keep the fast result."""
+    rng = np.random.default_rng(56)
+    vt = np.zeros((40, 36, 32), np.uint8)
+    vp = np.zeros((40, 36, 32), np.uint8)
+    vt[5:20, 4:30, 3:29] = 1                           # class 1: two boxes one or two voxels apart (near)
+    vp[6:21, 5:30, 2:28] = 1
+    vt[25:38, 2:10, 2:12] = 2                          # class 2: the prediction has an extra island 20 voxels away (far)
+    vp[25:38, 2:10, 2:12] = 2
+    vp[26:30, 30:34, 24:30] = 2
+    vt[22, 20:24, 16] = 3                              # class 3: exactly at the cap: distance 11 along one axis
+    vp[22, 20:24, 27] = 3
+    _check(vt, vp, 4, cuda)
+    # distances 10 (below the cap) and 11 (at the cap) along each axis in turn
+    for axis in range(3):
+        for gap in (10, 11):
+            a = np.zeros((48, 48, 48), np.uint8)
+            b = np.zeros((48, 48, 48), np.uint8)
+            idx = [slice(20, 23)] * 3
+            a[tuple(idx)] = 1
+            idx[axis] = slice(20 + 2 + gap, 23 + 2 + gap)
+            b[tuple(idx)] = 1
+            _check(a, b, 2, cuda)
+    # random surfaces with D2 = 16: dense enough that everything is near
+    vt = (rng.random((24, 20, 16)) < 0.5).astype(np.uint8)
+    vp = (rng.random((24, 20, 16)) < 0.5).astype(np.uint8)
+    _check(vt, vp, 2, cuda)
