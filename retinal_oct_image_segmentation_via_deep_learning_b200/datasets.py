@@ -5,6 +5,9 @@ the published file formats, not reference lines:
 * MetaImage ``.mhd`` + ``.raw`` / ``.zraw`` (RETOUCH volumes and reference masks): ``read_mhd`` / ``write_mhd``;
 * MATLAB ``.mat`` with boundary annotations (Duke DME / AMD: ``manualLayers1`` of shape boundaries x columns x
   B-scans, NaN where a column is not annotated): ``read_mat_layers``;
+* Heidelberg Spectralis raw export ``.vol`` (HC-MS, reference ``Datasets.md:13``; also AROI-style Spectralis data):
+  ``read_heidelberg_vol`` -- B-scan stack plus the device's own boundary lines;
+* HC-MS manual delineations (``.mat`` with ``bd_pts``: columns x B-scans x 9 boundaries): ``read_hcms_delineation``;
 * ``.npy`` / ``.npz`` label volumes: ``read_labels``.
 
 Everything here is plain host I/O (numpy, scipy.io for ``.mat``); the arrays go to the GPU through
@@ -121,6 +124,79 @@ def read_mat_layers(path, key=None):
     if "images" in mat and np.asarray(mat["images"]).ndim == 3:
         images = np.transpose(np.asarray(mat["images"]), (2, 0, 1))     # rows x columns x B-scans on disk
     return np.ascontiguousarray(layers), images
+
+
+_VOL_HEADER = 2048          # bytes; little-endian throughout
+_VOL_INVALID = 3.0e38       # Heidelberg marks missing samples / boundary points with FLT_MAX
+
+
+def read_heidelberg_vol(path):
+    """Heidelberg Engineering raw export (``.vol``, "HSF-OCT-1xx") -> dict with
+
+    * ``bscans``      float32 ``[NumBScans, SizeZ, SizeX]`` (rows = depth samples, invalid samples NaN),
+    * ``boundaries``  float32 ``[NumBScans, NumSeg, SizeX]`` -- the device's own boundary lines in pixels (ILM, BM, ...;
+      NaN where the device found none), ready for ``suite.labels_from_boundaries`` / ``suite.boundary_metrics``,
+    * ``scale``       (ScaleX, Distance between B-scans, ScaleZ) in mm, and ``header`` with the raw fields read.
+
+    Layout (file header 2048 B, then the SLO image, then per B-scan a header of ``BScanHdrSize`` bytes followed by
+    ``SizeX * SizeZ`` float32 samples): version 12s @0, SizeX i @12, NumBScans i @16, SizeZ i @20, ScaleX d @24,
+    Distance d @32, ScaleZ d @40, SizeXSlo i @48, SizeYSlo i @52, ..., BScanHdrSize i @100; B-scan header: version
+    12s @0, BScanHdrSize i @12, StartX/StartY/EndX/EndY d @16..47, NumSeg i @48, OffSeg i @52, Quality f @56, boundary
+    lines = NumSeg x SizeX float32 at OffSeg.  Written from the published description of the format; no Spectralis file
+    is available offline, the reader is exercised on files synthesised by the tests with the same layout."""
+    import struct
+    with open(path, "rb") as f:
+        blob = f.read()
+    if len(blob) < _VOL_HEADER or not blob[:7] == b"HSF-OCT":
+        raise ValueError(f"{path}: not a Heidelberg .vol file (version field {blob[:12]!r})")
+    size_x, n_scans, size_z = struct.unpack_from("<iii", blob, 12)
+    scale_x, distance, scale_z = struct.unpack_from("<ddd", blob, 24)
+    slo_x, slo_y = struct.unpack_from("<ii", blob, 48)
+    (hdr_size,) = struct.unpack_from("<i", blob, 100)
+    if min(size_x, n_scans, size_z) < 1 or hdr_size < 64 or slo_x < 0 or slo_y < 0:
+        raise ValueError(f"{path}: implausible header (SizeX {size_x}, NumBScans {n_scans}, SizeZ {size_z}, BScanHdrSize {hdr_size})")
+    pos = _VOL_HEADER + slo_x * slo_y
+    per_scan = hdr_size + size_x * size_z * 4
+    if len(blob) < pos + n_scans * per_scan:
+        raise ValueError(f"{path}: file holds {len(blob)} bytes, header needs {pos + n_scans * per_scan}")
+    bscans = np.empty((n_scans, size_z, size_x), np.float32)
+    lines, n_seg_max = [], 0
+    for i in range(n_scans):
+        base = pos + i * per_scan
+        n_seg, off_seg = struct.unpack_from("<ii", blob, base + 48)
+        if n_seg < 0 or n_seg > 32 or off_seg < 0 or off_seg + n_seg * size_x * 4 > hdr_size:
+            raise ValueError(f"{path}: B-scan {i}: implausible NumSeg {n_seg} / OffSeg {off_seg}")
+        seg = np.frombuffer(blob, "<f4", n_seg * size_x, base + off_seg).reshape(n_seg, size_x).copy()
+        seg[seg > _VOL_INVALID] = np.nan
+        lines.append(seg)
+        n_seg_max = max(n_seg_max, n_seg)
+        img = np.frombuffer(blob, "<f4", size_x * size_z, base + hdr_size).reshape(size_z, size_x)
+        bscans[i] = np.where(img > _VOL_INVALID, np.nan, img)
+    boundaries = np.full((n_scans, n_seg_max, size_x), np.nan, np.float32)
+    for i, seg in enumerate(lines):
+        boundaries[i, :len(seg)] = seg
+    header = {"version": blob[:12].rstrip(b"\0").decode("latin-1"), "SizeX": size_x, "NumBScans": n_scans, "SizeZ": size_z,
+              "SizeXSlo": slo_x, "SizeYSlo": slo_y, "BScanHdrSize": hdr_size}
+    return {"bscans": bscans, "boundaries": boundaries, "scale": (scale_x, distance, scale_z), "header": header}
+
+
+def read_hcms_delineation(path, key=None):
+    """Manual delineation of one HC-MS scan (He et al., "Retinal layer parcellation of optical coherence tomography
+    images: data resource for multiple sclerosis and healthy controls"; reference ``Datasets.md:13``): a ``.mat`` file
+    whose ``bd_pts`` holds the 9 boundary positions (pixels along the A-scan) as columns x B-scans x boundaries
+    (1024 x 49 x 9).  Returns float32 ``[B-scans, boundaries, columns]`` -- the layout of BASELINE config 2 and of
+    ``suite.boundary_metrics`` / ``suite.labels_from_boundaries``.  ``control_pts`` (the annotator's sparse control
+    points, a cell array) is not needed for scoring and is ignored."""
+    from scipy.io import loadmat
+    mat = loadmat(path)
+    names = [key] if key else ["bd_pts", "bds", "boundaries"]
+    found = next((n for n in names if n in mat), None)
+    if found is None:
+        raise KeyError(f"{path}: none of {names} present (variables: {sorted(k for k in mat if not k.startswith('__'))})")
+    bd = np.asarray(mat[found], dtype=np.float32)
+    if bd.ndim != 3:
+        raise ValueError(f"{path}: {found} has shape {bd.shape}, expected columns x B-scans x boundaries")
+    return np.ascontiguousarray(np.transpose(bd, (1, 2, 0)))
 
 
 def annotated_scans(layers, min_fraction=0.5):
