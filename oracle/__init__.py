@@ -15,10 +15,12 @@ Pinning status
   from ``/root/reference/Metrics`` and writes ``tests/golden/*.npz``; the
   reference ships no tests or golden vectors of its own).
 * ``contours_oracle.find_contours`` (scikit-image marching squares, version
-  unpinned by the reference, scikit-image absent from this image):
-  PARITY UNPINNED -- restated from the published algorithm; squared distances
-  are cross-checked against ``scipy.ndimage.distance_transform_edt`` on the
-  doubled lattice, the contour topology only against its own invariants.
+  unpinned by the reference, scikit-image absent from this image, so it
+  cannot be executed): PINNED TO PUBLISHED VECTORS -- the known-answer
+  vectors scikit-image itself publishes (docstring doctest, ``test_binary``,
+  ``test_float``; ``tests/golden/skimage_published_vectors.json``) are
+  reproduced vertex for vertex, in order; squared distances are cross-checked
+  against ``scipy.ndimage.distance_transform_edt`` on the doubled lattice.
 * boundary extraction, 3-D surface distances: build-defined extensions with no
   reference counterpart.
 """
