@@ -24,6 +24,7 @@
 //                        kept as independent checks of the default path.
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1393,7 +1394,7 @@ constexpr int kLdPad = 32;            // empty columns on both sides of a table:
 constexpr int kLdRing = 512;          // odd-column query ring per warp (entries)
 constexpr int kLdShort = 64;          // vertex lists up to this length are searched by brute force in the fused kernel
 #ifndef OCTM_LD_MINB
-#define OCTM_LD_MINB 10
+#define OCTM_LD_MINB 8
 #endif
 
 struct LayeredDistParams {
@@ -1708,11 +1709,28 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
         }
     }
 
-    for (long long pair = blockIdx.x; pair < prm.n_pairs; pair += gridDim.x) {
+    for (long long pair0 = blockIdx.x; pair0 < prm.n_pairs; pair0 += gridDim.x) {
+      // PASS 1: the class of pixel (0, 0) and the class after it are bounded by the SAME boundary row (#{label <= c00}
+      // from below, #{label < c00 + 1} from above).  When both maps start with the same class, the CTA of that class
+      // also owns the next class's pair: if its (different) verification holds as well, the tables and therefore all
+      // distances are identical and the results are copied; otherwise the pair is measured in a second turn.
+      bool own_next = false;             // CTA-uniform
+      for (int rep = 0; rep < 2; ++rep) {
+        if (rep == 1 && !own_next) break;
+        const long long pair = pair0 + rep;
         if (PASS == 2 && prm.max_sq[pair * 2] != kNeedsSearch) continue;                 // CTA-uniform
         __syncthreads();                     // the previous pair is finished with the tables, the counters and s_*
         const long long item = pair / K;
         const int cls = static_cast<int>(pair - item * K);
+        if (PASS == 1 && rep == 0) {
+            const uint32_t ft = lane < K ? prm.first_pos[(item * 2 + 0) * K + lane] : OCTM_NO_SEED;
+            const uint32_t fq = lane < K ? prm.first_pos[(item * 2 + 1) * K + lane] : OCTM_NO_SEED;
+            const int c00t = __ffs(__ballot_sync(0xffffffffu, ft == 0u)) - 1, c00p = __ffs(__ballot_sync(0xffffffffu, fq == 0u)) - 1;
+            if (c00t >= 0 && c00t == c00p) {
+                if (cls == c00t + 1) break;                  // owned by the CTA of pair - 1
+                own_next = cls == c00t && cls + 1 < K;
+            }
+        }
         if (tid < 2) { s_vmax[tid] = 0; s_ok[tid] = 1; s_minkey[tid] = 0xffffffffu; s_cnt[tid] = 0; }
         if (tid == 2) s_bad = 0;
         const uint32_t unsorted = PASS == 1 ? prm.unsorted[item] : 0u;
@@ -1908,6 +1926,41 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     stats_from_counters(bins2 + warp * (kCountBins / 2), s_vmax[warp], static_cast<int>(warp ? cnt0 : cnt1), lane,
                                         prm.max_sq + pair * 2 + warp, prm.p95_sq + (pair * 2 + warp) * 2, prm.sum_dist + pair * 2 + warp);
                 if (tid >= 64 && tid < 66) prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
+                if (PASS == 1 && rep == 0 && own_next) {
+                    // the next class: same rows, so (a) holds and the path is the same; (b) its band must be thicker
+                    // than every step, (c) its first pixel must be the path's raster-first pixel
+                    __syncthreads();
+                    if (tid < 2) s_ok[tid] = 1;
+                    __syncthreads();
+                    {
+                        const int m = warp >> 1, c1 = cls + 1;
+                        const int* rows = (m ? prm.bnd_p : prm.bnd_t) + item * (K - 1) * static_cast<long long>(W);
+                        const int* orow = c1 < K - 1 ? rows + c1 * static_cast<long long>(W) : nullptr;
+                        const short* lo = tabs + (2 * m) * tab + kLdPad;
+                        bool ok = prm.first_pos[(item * 2 + m) * K + c1] == s_minkey[m];
+                        for (int x0 = (warp & 1) * 32; x0 < W; x0 += 64) {
+                            const int x = x0 + lane;
+                            if (x < W) {
+                                const int h = (lo[2 * x] + 1) >> 1;
+                                const int hl = (lo[2 * max(x - 1, 0)] + 1) >> 1, hn = (lo[2 * min(x + 1, W - 1)] + 1) >> 1;
+                                const int o = orow != nullptr ? orow[x] : prm.H;
+                                ok = ok && o >= max(hl, max(h, hn)) + 1;
+                            }
+                        }
+                        if (!__all_sync(0xffffffffu, ok) && lane == 0) s_ok[m] = 0;
+                    }
+                    __syncthreads();
+                    if (s_ok[0] && s_ok[1]) {
+                        if (tid < 2) {
+                            prm.n_pts[(pair + 1) * 2 + tid] = tid ? cnt1 : cnt0;
+                            prm.max_sq[(pair + 1) * 2 + tid] = prm.max_sq[pair * 2 + tid];
+                            prm.p95_sq[(pair + 1) * 4 + tid * 2] = prm.p95_sq[pair * 4 + tid * 2];
+                            prm.p95_sq[(pair + 1) * 4 + tid * 2 + 1] = prm.p95_sq[pair * 4 + tid * 2 + 1];
+                            prm.sum_dist[(pair + 1) * 2 + tid] = prm.sum_dist[pair * 2 + tid];
+                        }
+                        own_next = false;
+                    }
+                }
                 continue;
             }
             if constexpr (PASS == 1) if (!(badbits & 4u)) {
@@ -2041,6 +2094,7 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
             prm.max_sq[pair * 2 + (tid - 64)] = kNeedsSearch;
         }
         if (tid == 66) atomicAdd(prm.search_count, 1u);
+      }
     }
 }
 
@@ -2271,6 +2325,9 @@ extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y
         long long grid = n_pairs;
         const long long cap = static_cast<long long>(octm::sm_count()) * fit;
         if (grid > cap) grid = cap;
+        // a CTA strides over the pairs by the grid size: keep the stride coprime to the class count, or every CTA would
+        // meet one class only (and the classes differ: the class after pixel (0, 0)'s is usually a copy, not a search)
+        while (grid > 1 && std::gcd(grid, static_cast<long long>(num_classes)) != 1) --grid;
         OCTM_TIMED(pass == 1 ? "layered_distance_kernel" : "layered_distance_kernel_pass2", s)
             kern<<<static_cast<unsigned>(grid), octm::kLdWarps * 32, smem, s>>>(lp);
         return octm::check_launch("layered_distance_kernel");
