@@ -2322,6 +2322,8 @@ extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y
             cudaGetLastError();
             fit = 1;
         }
+        static const int env_ctas = [] { const char* e = getenv("OCTM_LD_CTAS"); return e ? atoi(e) : 0; }();
+        if (env_ctas > 0 && env_ctas < fit) fit = env_ctas;             // co-scheduling experiments
         long long grid = n_pairs;
         const long long cap = static_cast<long long>(octm::sm_count()) * fit;
         if (grid > cap) grid = cap;

@@ -910,6 +910,9 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
         cudaGetLastError();
         per_sm = 1;
     }
+    // OCTM_LP_CTAS caps the resident CTAs per SM (co-scheduling experiments: leave room for another kernel)
+    static const int env_ctas = [] { const char* e = getenv("OCTM_LP_CTAS"); return e ? atoi(e) : 0; }();
+    if (env_ctas > 0 && env_ctas < per_sm) per_sm = env_ctas;
     long long grid = static_cast<long long>(sm_count()) * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     OCTM_TIMED("label_pass_fast", stream) kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, tm_true, tm_pred);
