@@ -569,6 +569,9 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
             const int lc = lane * 4;
             const bool cv = warp * kStrip + lc < W;
             uint32_t sq[2 * NP], ab[2 * NP], th[2 * NP + 1];
+            uint32_t fkt[2 * NP + 1], fkp[2 * NP + 1];
+#pragma unroll
+            for (int j = 0; j < 2 * NP + 1; ++j) fkt[j] = fkp[j] = OCTM_NO_SEED;
 #pragma unroll
             for (int j = 0; j < 2 * NP; ++j) sq[j] = ab[j] = 0;
 #pragma unroll
@@ -590,6 +593,15 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { cut[i] = H - cut[i]; cup[i] = H - cup[i]; }
                     }
+                    if (SORT && !SEEDS) {
+                        // first raster position of class j in these columns IF the column is in class order: its pixels
+                        // start at row #{label < j} = H - #{label >= j}
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (pvt[i] > cut[i]) fkt[j] = min(fkt[j], static_cast<uint32_t>((H - pvt[i]) * W + warp * kStrip + lc + i));
+                            if (pvp[i] > cup[i]) fkp[j] = min(fkp[j], static_cast<uint32_t>((H - pvp[i]) * W + warp * kStrip + lc + i));
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int d = cut[i] - cup[i];
@@ -608,6 +620,26 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) th[2 * NP] += abs(pvt[i] - pvp[i]);
+                if (SORT && !SEEDS) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (pvt[i] > 0) fkt[2 * NP] = min(fkt[2 * NP], static_cast<uint32_t>((H - pvt[i]) * W + warp * kStrip + lc + i));
+                        if (pvp[i] > 0) fkp[2 * NP] = min(fkp[2 * NP], static_cast<uint32_t>((H - pvp[i]) * W + warp * kStrip + lc + i));
+                    }
+                }
+            }
+            if (SORT && !SEEDS && prm.first_pos != nullptr) {
+                // Seeds for free: on a map whose columns are in class order (the certificate) the first pixel of a class is
+                // the minimum over the columns of its first row.  Maps that turn out NOT to be in order get their seeds
+                // from first_pos_fix_kernel afterwards (a second read of those maps only).
+#pragma unroll
+                for (int c = 0; c < 2 * NP + 1; ++c) {
+                    if (c < K) {
+                        const uint32_t a = __reduce_min_sync(0xffffffffu, fkt[c]), b = __reduce_min_sync(0xffffffffu, fkp[c]);
+                        if (lane == 0 && a != OCTM_NO_SEED) atomicMin(prm.first_pos + (item * 2 + 0) * K + c, a);
+                        if (lane == 0 && b != OCTM_NO_SEED) atomicMin(prm.first_pos + (item * 2 + 1) * K + c, b);
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 2 * NP; ++j) {
@@ -789,6 +821,51 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
     }
 }
 
+// Seeds of the maps the certificate rejected: first raster position of every class by a scan of the labels (K <= 8,
+// item_elems % 16 == 0, 16-byte aligned maps: the shapes of the strip kernel).  One CTA per flagged (item, map); a thread
+// takes every 256th 16-byte group, in raster order, so a class it has met once can be ignored from then on -- and once it
+// has met all K classes it is done (uniform random maps end after a few groups).
+__global__ void __launch_bounds__(256) first_pos_fix_kernel(const uint8_t* __restrict__ yt, const uint8_t* __restrict__ yp,
+                                                            long long n_items, long long item_elems, int K,
+                                                            const uint32_t* __restrict__ unsorted, uint32_t* first_pos) {
+    __shared__ uint32_t s_first[8];
+    const uint32_t all = (1u << K) - 1u;
+    for (long long job = blockIdx.x; job < n_items * 2; job += gridDim.x) {
+        const long long item = job >> 1;
+        const int m = static_cast<int>(job & 1);
+        if (!((unsorted[item] >> m) & 1u)) continue;                  // CTA-uniform
+        __syncthreads();
+        if (threadIdx.x < 8) s_first[threadIdx.x] = OCTM_NO_SEED;
+        __syncthreads();
+        const uint4* L = reinterpret_cast<const uint4*>((m ? yp : yt) + item * item_elems);
+        const long long groups = item_elems >> 4;
+        uint32_t seen = 0;
+        for (long long g = threadIdx.x; g < groups && seen != all; g += 256) {
+            const uint4 w = __ldg(L + g);
+            // one-hot byte per label: two words share a PRMT selector (their labels in alternate nibbles)
+            const uint32_t x0 = (w.x & 0x0f0f0f0fu) | ((w.y & 0x0f0f0f0fu) << 4), x1 = (w.z & 0x0f0f0f0fu) | ((w.w & 0x0f0f0f0fu) << 4);
+            const uint32_t lo = 0x08040201u, hi = 0x80402010u;
+            uint32_t bits = (prmt(lo, hi, x0) | prmt(lo, hi, x0 >> 16)) | (prmt(lo, hi, x1) | prmt(lo, hi, x1 >> 16));
+            bits = (bits | (bits >> 16));
+            bits = (bits | (bits >> 8)) & 0xffu;
+            uint32_t fresh = bits & ~seen & all;
+            seen |= bits;
+            while (fresh) {
+                const int c = __ffs(fresh) - 1;
+                fresh &= fresh - 1;
+                const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+                uint32_t pos = 16;
+#pragma unroll
+                for (int i = 15; i >= 0; --i)
+                    if (((words[i >> 2] >> ((i & 3) * 8)) & 0xffu) == static_cast<uint32_t>(c)) pos = i;
+                atomicMin(&s_first[c], static_cast<uint32_t>(g * 16 + pos));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < K) first_pos[(item * 2 + m) * K + threadIdx.x] = s_first[threadIdx.x];
+    }
+}
+
 // K3: sums over columns of (bt - bp)^2 and |bt - bp| for int32 boundary arrays [n][Kb][W].
 __global__ void __launch_bounds__(256) boundary_error_kernel(const int* __restrict__ bt, const int* __restrict__ bp,
                                                              long long n_rows, int W, long long* sum_sq,
@@ -916,7 +993,16 @@ static int launch_fast(const LabelPassParams& p0, cudaStream_t stream) {
     long long grid = static_cast<long long>(sm_count()) * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     OCTM_TIMED("label_pass_fast", stream) kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, tm_true, tm_pred);
-    return check_launch("label_pass_fast");
+    if (int e = check_launch("label_pass_fast")) return e;
+    if (SORT && !SEEDS && p.first_pos != nullptr) {
+        long long fgrid = p.n_items * 2;
+        const long long fcap = static_cast<long long>(sm_count()) * 8;
+        if (fgrid > fcap) fgrid = fcap;
+        OCTM_TIMED("first_pos_fix_kernel", stream) first_pos_fix_kernel<<<static_cast<unsigned>(fgrid), 256, 0, stream>>>(
+            p.yt, p.yp, p.n_items, static_cast<long long>(p.H) * p.W, p.K, p.unsorted, p.first_pos);
+        return check_launch("first_pos_fix_kernel");
+    }
+    return OCTM_OK;
 }
 
 template <bool CONF, bool COLS, bool SEEDS, bool SORT>
@@ -957,7 +1043,8 @@ int run_label_pass(const LabelPassParams& p, bool conf, bool cols, bool seeds, c
     if (fast_ok(p.H, p.W, p.K, p.yt, p.yp) && p.n_items * p.H < (1ll << 31) /* TMA row coordinate */ &&
         (p.bnd_t == nullptr || reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0) &&
         (p.bnd_p == nullptr || reinterpret_cast<uintptr_t>(p.bnd_p) % 16 == 0)) {
-        if (p.unsorted != nullptr) return dispatch_np<true, true, true, true>(p, stream);     // the suite's call: everything
+        // the suite's call: certificate; seeds (if asked for) from the column totals, rescanned for rejected maps
+        if (p.unsorted != nullptr) return dispatch_np<true, true, false, true>(p, stream);
         if (conf && cols && seeds) return dispatch_np<true, true, true, false>(p, stream);
         if (conf && cols) return dispatch_np<true, true, false, false>(p, stream);
         if (conf && !cols && !seeds) return dispatch_np<true, false, false, false>(p, stream);
@@ -1001,8 +1088,8 @@ extern "C" int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y
     p.bsq = reinterpret_cast<long long*>(bnd_sq);
     p.babs = reinterpret_cast<long long*>(bnd_abs);
     p.bnd_t = bnd_true; p.bnd_p = bnd_pred; p.first_pos = first_pos; p.unsorted = unsorted;
-    if (unsorted != nullptr && !(counts && thick_absdiff && bnd_sq && bnd_abs && first_pos))
-        return octm::fail(OCTM_ERR_INVALID, "unsorted needs counts, the column sums and first_pos (the full pass)");
+    if (unsorted != nullptr && !(counts && thick_absdiff && bnd_sq && bnd_abs))
+        return octm::fail(OCTM_ERR_INVALID, "unsorted needs counts and the column sums");
     const bool conf = counts != nullptr;
     const bool cols = thick_absdiff || bnd_sq || bnd_abs || bnd_true;
     const bool seeds = first_pos != nullptr;

@@ -19,17 +19,24 @@ def _first_pos_oracle(lab, k):
     return out
 
 
-def _run(yt, yp, k, cuda, boundaries=True):
+def _run(yt, yp, k, cuda, boundaries=True, certify=False):
     import torch
     from retinal_oct_image_segmentation_via_deep_learning_b200 import suite
     t, p = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
-    out = suite.label_pass(t, p, k, counts=True, columns=True, seeds=True, boundaries=boundaries)
+    out = suite.label_pass(t, p, k, counts=True, columns=True, seeds=True, boundaries=boundaries, certify=certify)
     torch.cuda.synchronize()
     return out
 
 
 def _check(yt, yp, k, cuda):
-    out = _run(yt, yp, k, cuda)
+    # certify=False: seeds tracked pixel by pixel; certify=True (the suite's call): seeds from the column totals on maps
+    # in class order, from a rescan on the others -- same outputs either way
+    _check_one(yt, yp, k, cuda, False)
+    _check_one(yt, yp, k, cuda, True)
+
+
+def _check_one(yt, yp, k, cuda, certify):
+    out = _run(yt, yp, k, cuda, certify=certify)
     n = yt.shape[0]
     ref = [lo.score_bscan_fast(yt[i], yp[i], k) for i in range(n)]
     np.testing.assert_array_equal(out.counts.cpu().numpy().view(np.uint64), np.stack([r["confusion"] for r in ref]))
