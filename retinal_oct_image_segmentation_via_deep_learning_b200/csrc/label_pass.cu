@@ -840,8 +840,7 @@ __global__ void __launch_bounds__(256) first_pos_fix_kernel(const uint8_t* __res
         const uint4* L = reinterpret_cast<const uint4*>((m ? yp : yt) + item * item_elems);
         const long long groups = item_elems >> 4;
         uint32_t seen = 0;
-        for (long long g = threadIdx.x; g < groups && seen != all; g += 256) {
-            const uint4 w = __ldg(L + g);
+        auto take = [&](const uint4& w, long long g) {
             // one-hot byte per label: two words share a PRMT selector (their labels in alternate nibbles)
             const uint32_t x0 = (w.x & 0x0f0f0f0fu) | ((w.y & 0x0f0f0f0fu) << 4), x1 = (w.z & 0x0f0f0f0fu) | ((w.w & 0x0f0f0f0fu) << 4);
             const uint32_t lo = 0x08040201u, hi = 0x80402010u;
@@ -860,7 +859,16 @@ __global__ void __launch_bounds__(256) first_pos_fix_kernel(const uint8_t* __res
                     if (((words[i >> 2] >> ((i & 3) * 8)) & 0xffu) == static_cast<uint32_t>(c)) pos = i;
                 atomicMin(&s_first[c], static_cast<uint32_t>(g * 16 + pos));
             }
+        };
+        long long g = threadIdx.x;
+        for (; g + 3 * 256 < groups && seen != all; g += 4 * 256) {     // four loads in flight per thread, taken in raster order
+            const uint4 w0 = __ldg(L + g), w1 = __ldg(L + g + 256), w2 = __ldg(L + g + 512), w3 = __ldg(L + g + 768);
+            take(w0, g);
+            take(w1, g + 256);
+            take(w2, g + 512);
+            take(w3, g + 768);
         }
+        for (; g < groups && seen != all; g += 256) take(__ldg(L + g), g);
         __syncthreads();
         if (threadIdx.x < K) first_pos[(item * 2 + m) * K + threadIdx.x] = s_first[threadIdx.x];
     }
