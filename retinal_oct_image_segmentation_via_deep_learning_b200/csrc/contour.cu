@@ -1412,6 +1412,7 @@ struct LayeredDistParams {
     double* sum_dist;            // [n][K][2]
     uint32_t* todo_count;        // PASS 1: += 1 per pair handed on (zeroed by the host)
     uint32_t* search_count;      // += 1 per pair left to the vertex-list search (zeroed by the host)
+    int vals_cap;                // PASS 2: entries of the per-CTA value list behind the rings (0: none, recompute instead)
 };
 
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
@@ -1534,10 +1535,19 @@ struct WideCounter {          // PASS 2 only: one code path for the three roles,
     uint32_t run_max = 0, next_min = 0xffffffffu;
     double sum = 0.0;
     bool run_bad = false, overflow = false;
+    uint32_t* vals = nullptr;     // coarse role: every value is also appended here (shared memory; any order), so that the
+    uint32_t* vals_n = nullptr;   // window role can run over the stored values instead of recomputing them
     __device__ __forceinline__ void add(int best, bool valid, int lane) {
         if (mode == 0) {
             count_minima(best, valid, lane, bins, run_max, run_bad);
             return;
+        }
+        if (mode == 1 && vals != nullptr) {
+            const uint32_t m = __ballot_sync(0xffffffffu, valid);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(vals_n, static_cast<uint32_t>(__popc(m)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (valid) vals[base + __popc(m & lanemask_lt())] = static_cast<uint32_t>(best);
         }
         const uint32_t v = static_cast<uint32_t>(best), key = v >> shift;
         if (valid) run_max = max(run_max, v);
@@ -1660,6 +1670,55 @@ __device__ __forceinline__ void ld_list_stats(const int* best, int n, int lane, 
     }
 }
 
+// PASS 2, one table and one short list: the direction whose QUERIES are the table's vertices, by the whole CTA without
+// rings or counters.  Thread t takes columns t, t + 128, ..: the even-column vertex and the run to the next column, every
+// query by brute force over the (at most 64) list vertices; the squared distances go to `vals` in shared memory (any
+// order), the sum of square roots and the maximum are kept per thread.  Order statistics by an 8-bit radix select over
+// the stored values (block_select, as in the single-kernel check modes).
+__device__ __forceinline__ void ld_table_vs_list(const short* qlo, const short* qhi, const int2* pts, int n, int W, int nq, int tid,
+                                                 uint32_t* vals, uint32_t* s_nvals, uint32_t* s_scr /*>= 8*/, double* s_dscr /*>= 8*/,
+                                                 uint32_t* s_hist /*256*/, uint32_t* s_bc /*2*/, uint32_t* max_sq, uint32_t* p95_sq,
+                                                 double* sum_dist) {
+    uint32_t vmax = 0;
+    double dsum = 0.0;
+    auto emit = [&](int qy, int qx) {
+        int best = 0x7fffffff;
+        for (int i = 0; i < n; ++i) {
+            const int2 v = pts[i];
+            const int dy = v.x - qy, dx = v.y - qx;
+            best = min(best, dy * dy + dx * dx);
+        }
+        vals[atomicAdd(s_nvals, 1u)] = static_cast<uint32_t>(best);
+        vmax = max(vmax, static_cast<uint32_t>(best));
+        dsum = __dadd_rn(dsum, sqrt(static_cast<double>(best) / 4.0));
+    };
+    for (int x = tid; x < W; x += kLdWarps * 32) {
+        emit(qlo[2 * x], 2 * x);
+        if (x + 1 < W)
+            for (int y = qlo[2 * x + 1], yh = qhi[2 * x + 1]; y <= yh; y += 2) emit(y, 2 * x + 1);
+    }
+    vmax = block_reduce_max<kLdWarps * 32>(vmax, s_scr);                  // (barriers inside: vals complete afterwards)
+    dsum = block_reduce_add<kLdWarps * 32>(dsum, s_dscr);
+    const double pos = __dmul_rn(static_cast<double>(nq - 1), 0.95);      // numpy linear percentile
+    const uint32_t lo = static_cast<uint32_t>(floor(pos));
+    const uint32_t v_lo = block_select<kLdWarps * 32>(vals, nq, lo, vmax, s_hist, s_bc);
+    uint32_t cnt_le = 0, next_gt = 0xffffffffu;
+    for (int j = tid; j < nq; j += kLdWarps * 32) {
+        const uint32_t v = vals[j];
+        cnt_le += v <= v_lo ? 1u : 0u;
+        if (v > v_lo) next_gt = min(next_gt, v);
+    }
+    cnt_le = block_reduce_add<kLdWarps * 32>(cnt_le, s_scr);
+    next_gt = block_reduce_min<kLdWarps * 32>(next_gt, s_scr);
+    const uint32_t v_hi = (lo + 1 >= static_cast<uint32_t>(nq) || cnt_le >= lo + 2) ? v_lo : next_gt;
+    if (tid == 0) {
+        *max_sq = vmax;
+        p95_sq[0] = v_lo;
+        p95_sq[1] = v_hi;
+        *sum_dist = dsum;
+    }
+}
+
 // The vertices of a table in column order -> verts (what trace_layered_kernel<true> would have written).
 __device__ __forceinline__ void ld_emit(const short* lo, const short* hi, int ncol, int lane, uint32_t* out, uint32_t cap) {
     uint32_t base = 0;
@@ -1693,7 +1752,8 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
     __shared__ int2 s_list[2][kLdShort];
     __shared__ int s_lbest[2][kLdShort];
     __shared__ double s_dsum[kLdWarps];
-    __shared__ uint32_t s_next, s_tgt[3], s_amax;
+    __shared__ double s_dsum8[8];
+    __shared__ uint32_t s_next, s_tgt[3], s_amax, s_nvals;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = prm.W, K = prm.K, tab = prm.tab, ncol = 2 * W - 1;
     if (PASS == 2 && *prm.todo_count == 0) return;
@@ -1898,6 +1958,24 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                 if (direct0) ld_list_stats(s_lbest[1], sd1.n, lane, prm.max_sq + pair * 2, prm.p95_sq + pair * 4, prm.sum_dist + pair * 2);
                 if (direct1) ld_list_stats(s_lbest[0], sd0.n, lane, prm.max_sq + pair * 2 + 1, prm.p95_sq + pair * 4 + 2, prm.sum_dist + pair * 2 + 1);
             }
+            if constexpr (PASS == 2) {
+                // one table, one short list: the table's vertices against the list without rings or counters
+                const int nq_tab = static_cast<int>(lay0 ? cnt0 : cnt1);
+                if (lay0 != lay1 && nq_tab <= prm.vals_cap) {
+                    const int d = lay0 ? 1 : 0;          // direction whose queries are the table
+                    uint32_t* const vals = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(tab) * 8 + kCountBins * 4 + kLdWarps * kLdRing * 4);
+                    if (tid == 0) s_nvals = 0;
+                    __syncthreads();
+                    ld_table_vs_list(lay0 ? sd0.lo : sd1.lo, lay0 ? sd0.hi : sd1.hi, lay0 ? s_list[1] : s_list[0],
+                                     static_cast<int>(lay0 ? cnt1 : cnt0), W, nq_tab, tid, vals, &s_nvals, bins2 + kCountBins /* scratch: warp 0's ring */,
+                                     s_dsum8, bins2, s_tgt, prm.max_sq + pair * 2 + d, prm.p95_sq + (pair * 2 + d) * 2,
+                                     prm.sum_dist + pair * 2 + d);
+                    __syncthreads();
+                    for (int i = tid; i < 256; i += kLdWarps * 32) bins2[i] = 0;       // block_select's histogram lives in the counters
+                    if (tid >= 64 && tid < 66) prm.n_pts[pair * 2 + (tid - 64)] = tid == 64 ? cnt0 : cnt1;
+                    continue;
+                }
+            }
 #pragma unroll 1
             for (int d = 0; d < 2; ++d) {
                 if (d ? direct1 : direct0) continue;
@@ -1995,11 +2073,16 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     if (tid < kLdWarps) s_dsum[tid] = 0.0;
                     if (tid == 0) { s_next = 0xffffffffu; s_amax = 0; }
                     __syncthreads();
+                    uint32_t* const vals = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(tab) * 8 + kCountBins * 4 + kLdWarps * kLdRing * 4);
+                    const bool stored = nq <= prm.vals_cap;              // CTA-uniform
+                    if (tid == 0) s_nvals = 0;
+                    __syncthreads();
                     WideCounter cc;
                     cc.bins = bins;
                     cc.mode = 1;
                     cc.shift = shift;
                     cc.target = 0;
+                    if (stored) { cc.vals = vals; cc.vals_n = &s_nvals; }
                     run_dir(d, cc);
                     {
                         const uint32_t wm = __reduce_max_sync(0xffffffffu, cc.run_max);
@@ -2045,7 +2128,14 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     wc.mode = 2;
                     wc.shift = shift;
                     wc.target = s_tgt[0];
-                    run_dir(d, wc);
+                    if (stored) {                        // over the stored values: no second enumeration
+                        for (int i0 = 0; i0 < nq; i0 += kLdWarps * 32) {
+                            const int i = i0 + tid;
+                            wc.add(i < nq ? static_cast<int>(vals[i]) : 0, i < nq, lane);
+                        }
+                    } else {
+                        run_dir(d, wc);
+                    }
                     const uint32_t wn = __reduce_min_sync(0xffffffffu, wc.next_min);
                     if (lane == 0) atomicMin(&s_next, wn);
                     __syncthreads();
@@ -2312,9 +2402,16 @@ extern "C" int octm_contour2d_metrics_u8(const uint8_t* y_true, const uint8_t* y
     uint32_t* search = todo + 1;
     const long long n_pairs = n_items * num_classes;
     octm::LayeredDistParams lp{first_pos, bnd_true, bnd_pred, unsorted, n_pairs, H, W, num_classes, max_pts, tab, verts,
-                               n_pts, max_sq, p95_sq, sum_dist, todo, search};
+                               n_pts, max_sq, p95_sq, sum_dist, todo, search, 0};
     auto launch_fused = [&](int pass) -> int {
         auto kern = pass == 1 ? octm::layered_distance_kernel<1> : octm::layered_distance_kernel<2>;
+        size_t smem_pass = smem;
+        lp.vals_cap = 0;
+        if (pass == 2 && max_pts <= 4096) {          // the second pass keeps a unit's distances in shared memory (wide counting)
+            smem_pass += static_cast<size_t>(max_pts) * 4;
+            lp.vals_cap = max_pts;
+        }
+        const size_t smem = smem_pass;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
             return octm::fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(layered_distance_kernel) failed");
         int fit = 0;

@@ -849,14 +849,16 @@ __global__ void __launch_bounds__(256) first_pos_fix_kernel(const uint8_t* __res
             bits = (bits | (bits >> 8)) & 0xffu;
             uint32_t fresh = bits & ~seen & all;
             seen |= bits;
-            while (fresh) {
+            while (fresh) {                                   // rare (a class is fresh once per thread and item)
                 const int c = __ffs(fresh) - 1;
                 fresh &= fresh - 1;
-                const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-                uint32_t pos = 16;
-#pragma unroll
-                for (int i = 15; i >= 0; --i)
-                    if (((words[i >> 2] >> ((i & 3) * 8)) & 0xffu) == static_cast<uint32_t>(c)) pos = i;
+                const uint32_t c4 = 0x01010101u * static_cast<uint32_t>(c);
+                auto zb = [&](uint32_t word) -> uint32_t {      // exact zero-byte test of word ^ c4
+                    const uint32_t x = word ^ c4;
+                    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+                };
+                const uint32_t z0 = zb(w.x), z1 = zb(w.y), z2 = zb(w.z), z3 = zb(w.w);
+                const uint32_t pos = z0 ? (__ffs(z0) - 1) >> 3 : (z1 ? 4 + ((__ffs(z1) - 1) >> 3) : (z2 ? 8 + ((__ffs(z2) - 1) >> 3) : 12 + ((__ffs(z3) - 1) >> 3)));
                 atomicMin(&s_first[c], static_cast<uint32_t>(g * 16 + pos));
             }
         };
