@@ -1832,7 +1832,42 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                 bool ok = true;
                 uint32_t minkey = 0xffffffffu, steps = 0;
                 const int H = prm.H;
-                for (int x0 = (warp & 1) * 32; x0 < W; x0 += 64) {
+                const bool vec4 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(hrow) | reinterpret_cast<uintptr_t>(orow)) & 15) == 0;
+                // four adjacent columns per lane (16-byte loads of the rows, one 16-byte store per table): a warp takes 128
+                // columns per turn; the columns left and right of a lane's four come from its neighbours
+                for (int x0 = (warp & 1) * 128; vec4 && x0 < W; x0 += 256) {
+                    const int x = x0 + 4 * lane;
+                    const int xc = min(x, W - 4);
+                    const int4 hv = *reinterpret_cast<const int4*>(hrow + xc);
+                    const int4 ov = orow != nullptr ? *reinterpret_cast<const int4*>(orow + xc) : (inv ? make_int4(0, 0, 0, 0) : make_int4(H, H, H, H));
+                    int hl = __shfl_up_sync(0xffffffffu, hv.w, 1), hn = __shfl_down_sync(0xffffffffu, hv.x, 1);
+                    if (lane == 0) hl = hrow[max(xc - 1, 0)];
+                    if (lane == 31) hn = hrow[min(xc + 4, W - 1)];
+                    if (x + 4 >= W) hn = hv.w;
+                    if (x < W) {
+                        const int hh[6] = {hl, hv.x, hv.y, hv.z, hv.w, hn};
+                        const int oo[4] = {ov.x, ov.y, ov.z, ov.w};
+                        uint32_t wl[4], wh[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int h = hh[i + 1], hp = hh[i], hx = hh[i + 2];
+                            if (PASS == 1) {
+                                const int lo_w = min(hp, min(h, hx)), hi_w = max(hp, max(h, hx));
+                                ok = ok && h >= 1 && h <= H - 1 && (inv ? oo[i] <= lo_w - 1 : oo[i] >= hi_w + 1);
+                                minkey = min(minkey, static_cast<uint32_t>(h) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x + i));
+                                steps += static_cast<uint32_t>(abs(hx - h));
+                            }
+                            const uint32_t e = static_cast<uint32_t>(2 * h - 1) & 0xffffu;
+                            const bool run = hx != h;
+                            wl[i] = e | ((run ? static_cast<uint32_t>(2 * min(h, hx)) & 0xffffu : 32767u) << 16);
+                            wh[i] = e | ((run ? static_cast<uint32_t>(2 * max(h, hx) - 2) & 0xffffu : 0x8000u) << 16);
+                        }
+                        // (the right neighbour of the last column is the column itself: no run, as in the scalar loop)
+                        *reinterpret_cast<uint4*>(lo32 + x) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                        *reinterpret_cast<uint4*>(hi32 + x) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                    }
+                }
+                for (int x0 = (warp & 1) * 32; !vec4 && x0 < W; x0 += 64) {
                     const int x = x0 + lane;
                     const int xc = min(x, W - 1);
                     const int h = hrow[xc];
