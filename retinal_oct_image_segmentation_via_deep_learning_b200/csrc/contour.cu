@@ -1421,12 +1421,12 @@ __device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b)
 // Nearest vertices of the tabulated contour (lo / hi point at column 0 of the tables) to TWO queries per lane: the
 // two scans share one loop (twice the loads in flight per pass, half the loop overhead per query).  A query whose
 // scan is over keeps folding in real distances, which is harmless.
-__device__ __forceinline__ void layered_nearest2(const short* lo, const short* hi, int qy0, int qx0, int qy1, int qx1,
-                                                 int ncol, int& best0, int& best1) {
-    const short* l0 = lo + qx0;
-    const short* h0 = hi + qx0;
-    const short* l1 = lo + qx1;
-    const short* h1 = hi + qx1;
+__device__ __forceinline__ void layered_nearest2p(const short* lo0, const short* hi0, const short* lo1, const short* hi1, int qy0,
+                                                  int qx0, int qy1, int qx1, int ncol, int& best0, int& best1) {
+    const short* l0 = lo0 + qx0;
+    const short* h0 = hi0 + qx0;
+    const short* l1 = lo1 + qx1;
+    const short* h1 = hi1 + qx1;
     const int dy0 = max3i(l0[0] - qy0, qy0 - h0[0], 0), dy1 = max3i(l1[0] - qy1, qy1 - h1[0], 0);
     best0 = dy0 * dy0;
     best1 = dy1 * dy1;
@@ -1451,14 +1451,18 @@ __device__ __forceinline__ void layered_nearest2(const short* lo, const short* h
     // contours further apart than the pad (rare): the same scan with clamped columns (the pads are empty columns)
     for (int e = d; e * e < best0; ++e) {
         const int cl = max(qx0 - e, -1), cr = min(qx0 + e, ncol), par = e & 1;
-        const int a0 = max3i(lo[cl] - qy0, qy0 - hi[cl], par), a1 = max3i(lo[cr] - qy0, qy0 - hi[cr], par);
+        const int a0 = max3i(lo0[cl] - qy0, qy0 - hi0[cl], par), a1 = max3i(lo0[cr] - qy0, qy0 - hi0[cr], par);
         best0 = min3i(best0, a0 * a0 + e * e, a1 * a1 + e * e);
     }
     for (int e = d; e * e < best1; ++e) {
         const int cl = max(qx1 - e, -1), cr = min(qx1 + e, ncol), par = e & 1;
-        const int a0 = max3i(lo[cl] - qy1, qy1 - hi[cl], par), a1 = max3i(lo[cr] - qy1, qy1 - hi[cr], par);
+        const int a0 = max3i(lo1[cl] - qy1, qy1 - hi1[cl], par), a1 = max3i(lo1[cr] - qy1, qy1 - hi1[cr], par);
         best1 = min3i(best1, a0 * a0 + e * e, a1 * a1 + e * e);
     }
+}
+__device__ __forceinline__ void layered_nearest2(const short* lo, const short* hi, int qy0, int qx0, int qy1, int qx1,
+                                                 int ncol, int& best0, int& best1) {
+    layered_nearest2p(lo, hi, lo, hi, qy0, qx0, qy1, qx1, ncol, best0, best1);
 }
 
 // Nearest vertices of a SHORT vertex list (shared memory, {y, x} pairs) to two queries: brute force.
@@ -1716,6 +1720,92 @@ __device__ __forceinline__ void ld_table_vs_list(const short* qlo, const short* 
         p95_sq[0] = v_lo;
         p95_sq[1] = v_hi;
         *sum_dist = dsum;
+    }
+}
+
+// PASS 1, both sides tables: BOTH directions in one go.  The even-column vertices of a direction are taken lane = column as
+// in ld_direction; the odd-column runs of both directions share the warp's ring (bit 31 of an entry = direction), so a
+// warp ends with ONE partially filled round instead of one per direction (the half-empty rounds were 10 % of the kernel).
+// side 0 = y_true's tables at tabs, side 1 = y_pred's at tabs + 2 tab; direction d: queries = side 1 - d, sources = side d.
+__device__ __forceinline__ void ld_both_tt(const short* tabs, int tab, int W, int ncol, int warp, int lane, uint32_t* ring,
+                                           uint32_t* bins2, uint32_t* s_vmax, uint32_t* s_bad) {
+    uint32_t rm0 = 0, rm1 = 0, head = 0, tail = 0;
+    bool bad0 = false, bad1 = false, overflow = false;
+    const int nblk = (W + 63) >> 6;
+    // count a squared distance of direction dirq (per lane) like count_minima, the two directions' counters side by side
+    auto count = [&](int bestd, bool valid, uint32_t dirq) {
+        const uint32_t dv = static_cast<uint32_t>(bestd), h = dv >> 1;
+        const bool ok = valid && (dv & 1u) == 0 && h < static_cast<uint32_t>(kCountBins);
+        const uint32_t peers = __match_any_sync(0xffffffffu, ok ? (h | (dirq << 16)) : 0x100000u + lane);
+        if (ok && lane == __ffs(peers) - 1)
+            atomicAdd(&bins2[dirq * (kCountBins / 2) + (h >> 1)], static_cast<uint32_t>(__popc(peers)) << ((h & 1u) * 16));
+        if (valid) {
+            if (dirq) rm1 = max(rm1, dv); else rm0 = max(rm0, dv);
+            if (!ok) { if (dirq) bad1 = true; else bad0 = true; }
+        }
+    };
+    auto ring_round = [&](uint32_t left) {
+        const bool v0 = static_cast<uint32_t>(lane) < left, v1 = static_cast<uint32_t>(lane) + 32u < left;
+        // idle slots repeat a source vertex of direction 0 (distance 0 at d = 0)
+        const uint32_t idle = static_cast<uint32_t>(static_cast<unsigned short>(tabs[kLdPad])) << 16;
+        const uint32_t q0 = v0 ? ring[(head + lane) & (kLdRing - 1)] : idle, q1 = v1 ? ring[(head + 32 + lane) & (kLdRing - 1)] : idle;
+        head += left < 64u ? left : 64u;
+        const uint32_t d0 = q0 >> 31, d1 = q1 >> 31;
+        const short* lo0 = tabs + kLdPad + d0 * (2 * tab);
+        const short* lo1 = tabs + kLdPad + d1 * (2 * tab);
+        int b0, b1;
+        layered_nearest2p(lo0, lo0 + tab, lo1, lo1 + tab, static_cast<int>((q0 >> 16) & 0x7fffu), static_cast<int>(q0 & 0xffffu),
+                          static_cast<int>((q1 >> 16) & 0x7fffu), static_cast<int>(q1 & 0xffffu), ncol, b0, b1);
+        count(b0, v0, d0);
+        count(b1, v1, d1);
+    };
+#pragma unroll 1
+    for (int dir = 0; dir < 2 && !overflow; ++dir) {
+        const short* slo = tabs + kLdPad + dir * (2 * tab);
+        const short* shi = slo + tab;
+        const short* qlo = tabs + kLdPad + (1 - dir) * (2 * tab);
+        const short* qhi = qlo + tab;
+        const uint32_t tag = static_cast<uint32_t>(dir) << 31;
+        const int idle_y = slo[0];
+        for (int blk = warp; blk < nblk; blk += kLdWarps) {          // 64 columns: lane takes x and x + 32
+            const int xa = blk * 64 + lane, xb = xa + 32;
+            const bool va = xa < W, vb = xb < W;
+            int ba, bb;
+            layered_nearest2(slo, shi, va ? qlo[2 * xa] : idle_y, va ? 2 * xa : 0, vb ? qlo[2 * xb] : idle_y, vb ? 2 * xb : 0, ncol, ba, bb);
+            count(ba, va, static_cast<uint32_t>(dir));
+            count(bb, vb, static_cast<uint32_t>(dir));
+            const bool ra = xa + 1 < W, rb = xb + 1 < W;
+            const int la = ra ? qlo[2 * xa + 1] : 32767, ha = ra ? qhi[2 * xa + 1] : -32768;
+            const int lb = rb ? qlo[2 * xb + 1] : 32767, hb = rb ? qhi[2 * xb + 1] : -32768;
+            const uint32_t lena = ha >= la ? static_cast<uint32_t>((ha - la) >> 1) + 1u : 0u;
+            const uint32_t lenb = hb >= lb ? static_cast<uint32_t>((hb - lb) >> 1) + 1u : 0u;
+            const uint32_t len = lena + lenb;
+            uint32_t incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total > static_cast<uint32_t>(kLdRing - 64)) { overflow = true; break; }   // absurdly steep: general path
+            uint32_t at = tail + incl - len;
+            for (uint32_t t = 0; t < lena; ++t, ++at)
+                ring[at & (kLdRing - 1)] = tag | (static_cast<uint32_t>(la + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xa + 1);
+            for (uint32_t t = 0; t < lenb; ++t, ++at)
+                ring[at & (kLdRing - 1)] = tag | (static_cast<uint32_t>(lb + 2 * static_cast<int>(t)) << 16) | static_cast<uint32_t>(2 * xb + 1);
+            tail += total;
+            __syncwarp();
+            while (tail - head >= 64u) ring_round(64u);
+            __syncwarp();
+        }
+    }
+    if (!overflow && tail != head) ring_round(tail - head);
+    const uint32_t w0 = __reduce_max_sync(0xffffffffu, rm0), w1 = __reduce_max_sync(0xffffffffu, rm1);
+    const bool b0 = __any_sync(0xffffffffu, bad0), b1 = __any_sync(0xffffffffu, bad1), ov = __any_sync(0xffffffffu, overflow);
+    if (lane == 0) {
+        atomicMax(&s_vmax[0], w0);
+        atomicMax(&s_vmax[1], w1);
+        if (b0 || b1 || ov) atomicOr(s_bad, (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (ov ? 4u : 0u));
     }
 }
 
@@ -2011,8 +2101,9 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                     continue;
                 }
             }
+            if constexpr (PASS == 1) ld_both_tt(tabs, tab, W, ncol, warp, lane, ring, bins2, s_vmax, &s_bad);
 #pragma unroll 1
-            for (int d = 0; d < 2; ++d) {
+            for (int d = PASS == 1 ? 2 : 0; d < 2; ++d) {
                 if (d ? direct1 : direct0) continue;
                 Counter fc;
                 fc.bins = bins2 + d * (kCountBins / 2);
