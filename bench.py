@@ -51,15 +51,24 @@ CONFIGS = {
 }
 KERNEL_NOTES = {
     # bound + the counter that shows it (ncu summaries under profiles/)
-    "label_pass_fast": ("hbm", "dram read = algorithmic bytes (ratio 1.01); issue-active 68 %: in-order issue at 4 warps/scheduler"),
-    "label_pass_generic": ("hbm", "thread-per-column run-length scan; latency-bound below ~1k items"),
-    "trace_layered_kernel": ("latency", "verification against label pixels, only for contours the boundary-row check rejects; returns at once on clean layered data"),
-    "layered_distance_kernel": ("issue", "boundary-row verification + shared-memory column tables; issue-active 72 %, DRAM 1.8 % of peak (r2b): 19 k warp-instructions per pair, a third of them scan passes kept alive by the slowest of a warp's 64 queries"),
-    "trace_kernel": ("latency", "serial walk, first-touch label loads"),
-    "distance_column_kernel": ("issue", "DRAM 6.5 % of peak, issue-active 68 %, barrier stall largest (r1_v10)"),
+    "label_pass_fast": ("hbm", "dram read = algorithmic bytes (ratio 1.01); issue-active 67 %: in-order issue at 4 warps/scheduler, 128 registers (r2)"),
+    "label_pass_generic": ("hbm", "thread-per-column run-length scan (K > 8, ragged widths); latency-bound below ~1k items"),
+    "first_pos_fix_kernel": ("hbm", "rescans only the maps the layering certificate rejected (nothing on clean data): 3.9 TB/s of those maps"),
+    "layered_distance_kernel": ("issue", "boundary-row verification + shared-memory column tables + fused distances; issue-active 72 %, DRAM 1.8 % of peak: 19 k warp-instructions per pair before the 4-column table build and the shared-contour copy (r2)"),
+    "layered_distance_kernel_pass2": ("issue", "pairs handed on (noisy predictions): tables x short vertex lists, wide counting; barrier-bound; returns at once on clean data"),
+    "trace_layered_kernel": ("latency", "verification against label pixels with re-centred rows, only for contours the boundary-row check rejects; returns at once on clean layered data"),
+    "trace_kernel": ("latency", "serial walk, first-touch label loads; only what is not a height function"),
+    "distance_column_kernel": ("issue", "vertex-list search, only long x long lists (lesions); DRAM 6.5 % of peak, issue-active 68 % (r1_v10)"),
     "distance_select_kernel": ("latency", "only units the counters cannot hold"),
     "derive_kernel": ("hbm", "streams the integer outputs once"),
     "totals_kernel": ("latency", "one CTA per output element"),
+    "near_surface_kernel": ("hbm", "surface bits: 16 voxels per thread, five label lines (L2 reuse between neighbouring lines)"),
+    "near_pass1_kernel": ("issue", "distance to the nearest surface bit within +-10 from three 16-bit words (BREV / FFS)"),
+    "near_pass2_kernel": ("issue", "windowed min-plus along D1, VIADDMNMX.U16x2: 672 per thread for 64 voxels"),
+    "near_pass3_kernel": ("latency", "windowed min-plus along D0 at the query-surface voxels only (tiles without a query bit are skipped)"),
+    "edt3_pass1_vec_kernel": ("latency", "general (Meijster) path: only units with a distance >= 11 voxels; returns at once otherwise"),
+    "edt3_pass2_kernel": ("latency", "general path, see above"),
+    "edt3_pass3_kernel": ("latency", "general path, see above"),
 }
 
 
