@@ -189,7 +189,7 @@ _REF = None
 
 
 def _ref_functions():
-    """The unmodified reference modules (baseline/_ref/Metrics or /root/reference/Metrics) + restated contours,
+    """The unmodified reference modules (baseline/_ref/Metrics, installed by __graft_entry__.build()) + restated contours,
     or None -> the oracle port."""
     global _REF
     if _REF is None:

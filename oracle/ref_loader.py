@@ -11,7 +11,8 @@ import importlib.util
 import os
 import types
 
-SEARCH = ("/root/reference/Metrics", os.path.join(os.path.dirname(__file__), "..", "baseline", "_ref", "Metrics"))
+# the installed copy first (it travels to the GPU box; bench.py's reference arm uses it), the checkout for the CPU tests
+SEARCH = (os.path.join(os.path.dirname(__file__), "..", "baseline", "_ref", "Metrics"), "/root/reference/Metrics")
 
 
 def _import(path, name):

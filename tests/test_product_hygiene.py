@@ -19,8 +19,15 @@ def test_product_package_never_imports_the_oracle():
 
 
 def test_gpu_tests_and_bench_do_not_read_the_reference_checkout():
-    for f in ("bench.py", "__graft_entry__.py"):
-        assert "/root/reference" not in open(os.path.join(ROOT, f)).read()
+    assert "/root/reference" not in open(os.path.join(ROOT, "bench.py")).read()
+    # __graft_entry__.build() installs the reference's Metrics/ into baseline/_ref in the build container (the one
+    # place that may name the checkout); smoke() runs on the GPU box and must not
+    import inspect
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("graft_entry_check", os.path.join(ROOT, "__graft_entry__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert "/root/reference" not in inspect.getsource(mod.smoke)
     for f in os.listdir(os.path.join(ROOT, "tests")):
         if f.startswith("test_gpu"):
             assert "/root/reference" not in open(os.path.join(ROOT, "tests", f)).read()
