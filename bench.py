@@ -51,10 +51,10 @@ CONFIGS = {
 }
 KERNEL_NOTES = {
     # bound + the counter that shows it (ncu summaries under profiles/)
-    "label_pass_fast": ("hbm", "dram read = algorithmic bytes (ratio 1.01); issue-active 67 %: in-order issue at 4 warps/scheduler, 128 registers (r2)"),
+    "label_pass_fast": ("hbm", "dram read = algorithmic bytes (ratio 1.01); issue-active 70.5 %, 109 k warp-instructions per B-scan: in-order issue at 4 warps/scheduler, 128 registers (r2)"),
     "label_pass_generic": ("hbm", "thread-per-column run-length scan (K > 8, ragged widths); latency-bound below ~1k items"),
     "first_pos_fix_kernel": ("hbm", "rescans only the maps the layering certificate rejected (nothing on clean data): 3.9 TB/s of those maps"),
-    "layered_distance_kernel": ("issue", "boundary-row verification + shared-memory column tables + fused distances; issue-active 72 %, DRAM 1.8 % of peak: 19 k warp-instructions per pair before the 4-column table build and the shared-contour copy (r2)"),
+    "layered_distance_kernel": ("issue", "boundary-row verification + shared-memory column tables + fused distances; issue-active 75 %, DRAM 2 % of peak: 16.4 k warp-instructions per (B-scan, class) pair (r2)"),
     "layered_distance_kernel_pass2": ("issue", "pairs handed on (noisy predictions): tables x short vertex lists, wide counting; barrier-bound; returns at once on clean data"),
     "trace_layered_kernel": ("latency", "verification against label pixels with re-centred rows, only for contours the boundary-row check rejects; returns at once on clean layered data"),
     "trace_kernel": ("latency", "serial walk, first-touch label loads; only what is not a height function"),
