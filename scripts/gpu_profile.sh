@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r2}
-SMALL="--items 2048 --steps 2 --warmup 1 --no-e2e --no-cpu --no-secondary"
+SMALL="--items 2048 --steps 3 --warmup 3 --no-e2e --no-cpu --no-secondary"
 python bench.py > gpurun_out/bench_cfg4_$TAG.json 2> gpurun_out/bench_cfg4_$TAG.err
 for c in cfg1 cfg2 cfg3 cfg5; do python bench.py --config $c --steps 5 > gpurun_out/bench_${c}_$TAG.json 2> gpurun_out/bench_${c}_$TAG.err; done
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_$TAG.json 2> gpurun_out/bench_reference_$TAG.err
@@ -14,7 +14,7 @@ python bench.py $SMALL > gpurun_out/bench_small_$TAG.json 2> gpurun_out/bench_sm
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py $SMALL > gpurun_out/ncu_launches_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'label_pass_fast|layered_distance_kernel|derive_kernel|totals_kernel' -s 8 -c 4 \
+    -k regex:'label_pass_fast|layered_distance_kernel|derive_kernel|totals_kernel' -s 16 -c 4 \
     -o gpurun_out/prof_$TAG python bench.py $SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on \
     -k regex:'argmax_planes|auc_kernel|rasterise_kernel|near_|layered_distance_kernel|trace_|distance_column' -c 24 \
