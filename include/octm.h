@@ -134,7 +134,8 @@ OCTM_API int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y_p
                               uint32_t* unsorted, void* stream);
 
 /* Which implementation octm_label_pass_u8 / K1 / K2 would use for this shape:
- * 1 = TMA-staged column-strip kernel, 0 = generic kernel. */
+ * 1 = TMA-staged column-strip kernel (K <= 8, W % 16 == 0), 2 = warp-per-strip run-length kernel (K <= 16, W % 4 == 0,
+ * 4-byte aligned maps), 0 = byte-wise generic kernel. */
 OCTM_API int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred);
 
 /* max label over the whole tensor -> *max_label (device uint32); for input validation. */

@@ -680,7 +680,10 @@ label_pass_fast(const LabelPassParams prm, const __grid_constant__ CUtensorMap t
 // the joint code (t, p) comes in long RUNS (a column stays inside a layer for many rows): only a run's length
 // is accumulated per pixel; when the code changes the run goes into the warp's shared-memory confusion
 // histogram (one atomic per run, not per pixel) and into the thread's own per-class column counters.
-__global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams prm, const int strips) {
+#ifndef OCTM_GEN_MINB
+#define OCTM_GEN_MINB 4
+#endif
+__global__ void __launch_bounds__(256, OCTM_GEN_MINB) label_pass_generic(const LabelPassParams prm, const int strips) {
     __shared__ uint32_t s_counts[8][256];                 // per-warp confusion histogram, code = t * 16 + p
     __shared__ unsigned short s_cls[2][16][256];          // per-thread class counts of the current column
     __shared__ unsigned long long s_sq[16], s_abs[16], s_thick[16];
@@ -701,17 +704,17 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
         __syncthreads();
         const uint8_t* bt = prm.yt + item * H * static_cast<long long>(W);
         const uint8_t* bp = prm.yp + item * H * static_cast<long long>(W);
-        // this thread's sums over its columns in 32 bits; squares go straight to the 64-bit shared sums when
-        // H^2 x (columns per thread) could overflow them
-        const bool wide = static_cast<unsigned long long>(H) * H * ((W + 255) / 256) >= (1ull << 32);
-        uint32_t acc_sq[15], acc_abs[15], acc_th[16];
-#pragma unroll
-        for (int j = 0; j < 15; ++j) acc_sq[j] = acc_abs[j] = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc_th[j] = 0;
-        for (int x = xbeg + tid; x < xend; x += 256) {
+        // a warp takes 32 adjacent columns at a time (uniform trip count: lanes past the last column run on empty counts);
+        // their sums meet in a warp reduction and one shared-memory atomic per quantity -- nothing is carried in
+        // registers across columns, which is what lets four CTAs share an SM (126 registers, two CTAs before)
+        const bool wide = static_cast<unsigned long long>(H) * H * 32ull >= (1ull << 32);
+        const int lane = tid & 31;
+        for (int x0 = xbeg + warp * 32; x0 < xend; x0 += 256) {
+            const int x = x0 + lane;
+            const bool valid = x < xend;
 #pragma unroll
             for (int c = 0; c < 16; ++c) s_cls[0][c][tid] = s_cls[1][c][tid] = 0;
+            if (valid) {
             uint32_t seen_t = 0, seen_p = 0;     // raster index grows with y inside one column
             uint32_t run_code = 0xffffffffu, run = 0;
             auto flush = [&]() {
@@ -724,9 +727,25 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
                     s_cls[1][p][tid] = static_cast<unsigned short>(s_cls[1][p][tid] + run);
                 }
             };
-#pragma unroll 4
-            for (int y = 0; y < H; ++y) {
-                const uint32_t t = bt[static_cast<long long>(y) * W + x], p = bp[static_cast<long long>(y) * W + x];
+            // the loads of kGenRows rows are issued before any of them is looked at: the run bookkeeping below has
+            // shared-memory atomics in it, which the compiler will not move loads across (2 loads in flight per thread
+            // otherwise: 280 GB/s)
+            constexpr int kGenRows = 8;
+            const uint8_t* ct = bt + x;
+            const uint8_t* cp = bp + x;
+            for (int y0 = 0; y0 < H; y0 += kGenRows) {
+                uint32_t tv[kGenRows], pv[kGenRows];
+#pragma unroll
+                for (int u = 0; u < kGenRows; ++u) {
+                    const long long off = static_cast<long long>(min(y0 + u, H - 1)) * W;
+                    tv[u] = __ldg(ct + off);
+                    pv[u] = __ldg(cp + off);
+                }
+#pragma unroll
+                for (int u = 0; u < kGenRows; ++u) {
+                const int y = y0 + u;
+                if (y >= H) break;
+                const uint32_t t = tv[u], p = pv[u];
                 const uint32_t code = t * 256u + p;
                 if (code != run_code) {
                     if (run_code != 0xffffffffu && ((t < (run_code >> 8)) || (p < (run_code & 255u))))
@@ -744,47 +763,34 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
                     }
                 }
                 ++run;
+                }
             }
             flush();
+            }
             // column arithmetic from the class counts: #{label >= k} by a suffix sum over the classes
             int ge_t = 0, ge_p = 0;
-#pragma unroll
-            for (int c = 15; c >= 0; --c) {
+#pragma unroll 1
+            for (int c = K - 1; c >= 0; --c) {
                 const int ct = s_cls[0][c][tid], cp = s_cls[1][c][tid];
-                if (c < K) acc_th[c] += static_cast<uint32_t>(abs(ct - cp));
+                const uint32_t th = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(abs(ct - cp)));
+                if (lane == 0 && th) atomicAdd(&s_thick[c], static_cast<unsigned long long>(th));
                 ge_t += ct;
                 ge_p += cp;
-                if (c >= 1 && c <= nthr) {                                  // threshold k = c
+                if (c >= 1) {                                               // threshold k = c
                     const int d = ge_t - ge_p;
-                    if (wide) atomicAdd(&s_sq[c - 1], static_cast<unsigned long long>(static_cast<long long>(d) * d));
-                    else acc_sq[c - 1] += static_cast<uint32_t>(d * d);
-                    acc_abs[c - 1] += static_cast<uint32_t>(abs(d));
-                    if (prm.bnd_t != nullptr) {
+                    const uint32_t ab = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(abs(d)));
+                    if (wide) {
+                        if (d) atomicAdd(&s_sq[c - 1], static_cast<unsigned long long>(static_cast<long long>(d) * d));
+                    } else {
+                        const uint32_t sq = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(d * d));
+                        if (lane == 0 && sq) atomicAdd(&s_sq[c - 1], static_cast<unsigned long long>(sq));
+                    }
+                    if (lane == 0 && ab) atomicAdd(&s_abs[c - 1], static_cast<unsigned long long>(ab));
+                    if (valid && prm.bnd_t != nullptr) {
                         prm.bnd_t[(item * nthr + (c - 1)) * W + x] = H - ge_t;
                         prm.bnd_p[(item * nthr + (c - 1)) * W + x] = H - ge_p;
                     }
                 }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 15; ++j) {
-            if (j < nthr) {
-                unsigned long long a64 = acc_sq[j], b64 = acc_abs[j];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    a64 += __shfl_xor_sync(0xffffffffu, a64, o);
-                    b64 += __shfl_xor_sync(0xffffffffu, b64, o);
-                }
-                if ((tid & 31) == 0) { atomicAdd(&s_sq[j], a64); atomicAdd(&s_abs[j], b64); }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            if (c < K) {
-                unsigned long long a64 = acc_th[c];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a64 += __shfl_xor_sync(0xffffffffu, a64, o);
-                if ((tid & 31) == 0) atomicAdd(&s_thick[c], a64);
             }
         }
         __syncthreads();
@@ -818,6 +824,229 @@ __global__ void __launch_bounds__(256) label_pass_generic(const LabelPassParams 
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ wide columns (K <= 16)
+// The shapes of HC-MS / Duke-style label sets (9-10 classes) that the strip kernel (K <= 8) does not take: H <= 16383,
+// K <= 16, W % 4 == 0, 4-byte aligned maps.  Same run-length idea as label_pass_generic, restructured so that the per-pixel
+// work is a few instructions per 128 pixels and the per-run work runs with all lanes busy:
+//   * a WARP owns a job = (item, 128-column strip): a lane reads 4 adjacent columns with one 32-bit load per map and
+//     row (a warp row = one 128-byte line per map), 8 rows x 2 maps in flight per lane, issued before any is used;
+//   * the (t, p) codes of the 4 columns are formed two at a time by PRMT (t << 8 | p in each half-word) and compared
+//     with the open runs' codes as packed words; a run's length is the difference of row numbers: nothing is counted
+//     per pixel;
+//   * a lane whose column changes class only PUSHES the finished run {length, column, t, p} onto its own queue in
+//     shared memory (six predicated instructions); ALL bookkeeping happens when the queues are drained in lockstep --
+//     entry i of every lane at once: confusion histogram (one shared atomic per run), the columns' class counts, the
+//     order check against the column's previous run and the first positions (private per-lane minima, no atomics;
+//     a column's row position is the sum of its runs so far).  Doing the bookkeeping where the change is met costs a
+//     divergent pass per row on which ANY of the 128 columns changes -- on tilted layers nearly every row (ncu: 0.67
+//     warp-instructions per pixel pair, the same as the byte-wise kernel);
+//   * column arithmetic, boundary rows (16-byte stores) and seeds follow per job; warps never meet: their results
+//     join in zero-initialised outputs through global atomics (a few hundred per 63 k pixel pairs).
+constexpr int kWideWarps = 2;
+constexpr int kWideQueue = 64;       // queue entries per lane; a batch of 8 rows pushes at most 32
+// per warp: counts u32 [256] | cls u16 [2][K][128] | queue u32 [kWideQueue][32] | fst u32 [2 K][32] | colstate u32 [4][32]
+// (sized by K: 17 KB per warp at K = 10 -> 12 warps per SM)
+static inline int wide_warp_bytes(int K) { return 1024 + 512 * K + kWideQueue * 128 + 256 * K + 512; }
+#ifndef OCTM_WIDE_MINB
+#define OCTM_WIDE_MINB 5
+#endif
+#ifndef OCTM_WIDE_ROWS
+#define OCTM_WIDE_ROWS 8
+#endif
+#ifndef OCTM_WIDE_PIPE
+#define OCTM_WIDE_PIPE 1
+#endif
+__global__ void __launch_bounds__(kWideWarps * 32, OCTM_WIDE_MINB) label_pass_wide(const LabelPassParams prm, const int strips) {
+    extern __shared__ __align__(16) unsigned char s_wide[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = prm.H, W = prm.W, K = prm.K, nthr = K - 1;
+    unsigned char* base = s_wide + warp * (1024 + 512 * K + kWideQueue * 128 + 256 * K + 512);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(base);
+    unsigned short* cls = reinterpret_cast<unsigned short*>(base + 1024);             // [(map * K + class) * 128 + column]
+    uint32_t* queue = reinterpret_cast<uint32_t*>(base + 1024 + 512 * K) + lane;      // entry i at queue[i * 32]: conflict-free
+    uint32_t* fst = reinterpret_cast<uint32_t*>(base + 1024 + 512 * K + kWideQueue * 128) + lane;   // [map * K + class][lane]
+    uint32_t* colstate = fst + 2 * K * 32;   // [column][lane]: rows so far (16 bits) | last run's t << 16 | its p << 24
+    const uint32_t uK = static_cast<uint32_t>(K);
+    const long long jobs = prm.n_items * strips;
+    // the warps of a CTA take adjacent strips of one item
+    for (long long job = static_cast<long long>(blockIdx.x) * kWideWarps + warp; job < jobs;
+         job += static_cast<long long>(gridDim.x) * kWideWarps) {
+        const long long item = job / strips;
+        const int x = static_cast<int>(job % strips) * 128 + 4 * lane;          // this lane's first column
+        const bool valid = x < W;                                               // W % 4 == 0: all four or none
+        {
+            uint4* z = reinterpret_cast<uint4*>(base);                          // counts + cls: 1024 + 512 K bytes
+#pragma unroll 1
+            for (int i = 0; i < 2 + K; ++i) z[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+            for (int i = 0; i < 2 * K; ++i) fst[i * 32] = OCTM_NO_SEED;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) colstate[i * 32] = 0xffff0000u;         // no rows yet, no previous run
+        }
+        __syncwarp();
+        uint32_t uns = 0;
+        int qn = 0;
+        auto drain = [&]() {                     // all lanes, entry i of every queue at once
+            const int most = __reduce_max_sync(0xffffffffu, qn);
+#pragma unroll 1
+            for (int i = 0; i < most; ++i) {
+                if (i < qn) {
+                    const uint32_t e = queue[i * 32];
+                    const uint32_t t = (e >> 8) & 255u, p = e & 255u, J = (e >> 16) & 3u, len = e >> 18;
+                    const uint32_t cs = colstate[J * 32];
+                    const uint32_t start = cs & 0xffffu, lt = (cs >> 16) & 255u, lp = cs >> 24;
+                    colstate[J * 32] = (start + len) | (t << 16) | (p << 24);
+                    if (lt != 255u) uns |= (t < lt ? 1u : 0u) | (p < lp ? 2u : 0u);
+                    const uint32_t pos = start * static_cast<uint32_t>(W) + static_cast<uint32_t>(x) + J;
+                    const uint32_t col = 4u * lane + J;
+                    if (t < uK) {
+                        fst[t * 32] = min(fst[t * 32], pos);
+                        if (p < uK) {                    // a run with a label >= K is dropped, never aliased
+                            atomicAdd(&counts[t * 16u + p], len);
+                            unsigned short* a = cls + t * 128u + col;
+                            unsigned short* b = cls + (uK + p) * 128u + col;
+                            *a = static_cast<unsigned short>(*a + len);
+                            *b = static_cast<unsigned short>(*b + len);
+                        }
+                    }
+                    if (p < uK) fst[(uK + p) * 32] = min(fst[(uK + p) * 32], pos);
+                }
+            }
+            qn = 0;
+        };
+        {
+            // lanes past the last column scan the last four columns again and push nothing
+            const int xc = valid ? x : W - 4;
+            const uint8_t* ct = prm.yt + item * H * static_cast<long long>(W) + xc;
+            const uint8_t* cp = prm.yp + item * H * static_cast<long long>(W) + xc;
+            constexpr int kRows = OCTM_WIDE_ROWS;
+            static_assert(4 * kRows <= kWideQueue, "a batch must fit the queue");
+            uint32_t ta[kRows], pa[kRows];
+            auto fetch = [&](uint32_t (&tv)[kRows], uint32_t (&pv)[kRows], int y0) {
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) {        // rows past the end repeat the last row: no change, nothing pushed
+                    const long long off = static_cast<long long>(min(y0 + u, H - 1)) * W;
+                    tv[u] = __ldg(reinterpret_cast<const uint32_t*>(ct + off));
+                    pv[u] = __ldg(reinterpret_cast<const uint32_t*>(cp + off));
+                }
+            };
+            fetch(ta, pa, 0);
+            // the runs open at row 0
+            uint32_t open01 = prmt(pa[0], ta[0], 0x5140u), open23 = prmt(pa[0], ta[0], 0x7362u);
+            int st0 = 0, st1 = 0, st2 = 0, st3 = 0;                    // first rows of the open runs
+            auto push = [&](uint32_t old, int& st, int y, uint32_t J) {
+                queue[qn * 32] = (static_cast<uint32_t>(y - st) << 18) | (J << 16) | old;
+                ++qn;
+                st = y;
+            };
+            auto work = [&](const uint32_t (&tv)[kRows], const uint32_t (&pv)[kRows], int y0) {
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) {
+                    const uint32_t c01 = prmt(pv[u], tv[u], 0x5140u), c23 = prmt(pv[u], tv[u], 0x7362u);
+                    const uint32_t d01 = c01 ^ open01, d23 = c23 ^ open23;
+                    if (valid && (d01 | d23) != 0u) {
+                        const int y = y0 + u;
+                        if (d01 & 0xffffu) push(open01 & 0xffffu, st0, y, 0u);
+                        if (d01 >> 16) push(open01 >> 16, st1, y, 1u);
+                        if (d23 & 0xffffu) push(open23 & 0xffffu, st2, y, 2u);
+                        if (d23 >> 16) push(open23 >> 16, st3, y, 3u);
+                        open01 = c01;
+                        open23 = c23;
+                    }
+                }
+            };
+#if OCTM_WIDE_PIPE
+            // two register batches: the loads of the next one are in flight while this one is worked on
+            uint32_t tb[kRows], pb[kRows];
+            for (int y0 = 0; y0 < H; y0 += 2 * kRows) {
+                fetch(tb, pb, y0 + kRows);
+                work(ta, pa, y0);
+                if (__any_sync(0xffffffffu, qn > kWideQueue - 4 * kRows)) drain();
+                fetch(ta, pa, y0 + 2 * kRows);
+                work(tb, pb, y0 + kRows);
+                if (__any_sync(0xffffffffu, qn > kWideQueue - 4 * kRows)) drain();
+            }
+#else
+            for (int y0 = 0; y0 < H; y0 += kRows) {
+                if (y0) fetch(ta, pa, y0);
+                work(ta, pa, y0);
+                if (__any_sync(0xffffffffu, qn > kWideQueue - 4 * kRows)) drain();
+            }
+#endif
+            if (valid) {                                               // the runs still open at the bottom
+                push(open01 & 0xffffu, st0, H, 0u);
+                push(open01 >> 16, st1, H, 1u);
+                push(open23 & 0xffffu, st2, H, 2u);
+                push(open23 >> 16, st3, H, 3u);
+            }
+            drain();
+        }
+        __syncwarp();
+        // column arithmetic from the class counts: #{label >= k} by a suffix sum over the classes, 4 columns per lane
+        {
+            int get[4] = {0, 0, 0, 0}, gep[4] = {0, 0, 0, 0};
+#pragma unroll 1
+            for (int c = K - 1; c >= 0; --c) {
+                const uint2 a = *reinterpret_cast<const uint2*>(cls + c * 128 + 4 * lane);
+                const uint2 b = *reinterpret_cast<const uint2*>(cls + (K + c) * 128 + 4 * lane);
+                const int ctv[4] = {static_cast<int>(a.x & 0xffffu), static_cast<int>(a.x >> 16), static_cast<int>(a.y & 0xffffu), static_cast<int>(a.y >> 16)};
+                const int cpv[4] = {static_cast<int>(b.x & 0xffffu), static_cast<int>(b.x >> 16), static_cast<int>(b.y & 0xffffu), static_cast<int>(b.y >> 16)};
+                uint32_t th = 0, ab = 0;
+                unsigned long long sq = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    th += static_cast<uint32_t>(abs(ctv[j] - cpv[j]));
+                    get[j] += ctv[j];
+                    gep[j] += cpv[j];
+                    const int d = get[j] - gep[j];
+                    ab += static_cast<uint32_t>(abs(d));
+                    sq += static_cast<unsigned long long>(static_cast<long long>(d) * d);
+                }
+                th = __reduce_add_sync(0xffffffffu, th);
+                if (lane == 0 && th && prm.thick != nullptr)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(prm.thick) + item * K + c, static_cast<unsigned long long>(th));
+                if (c >= 1) {                                               // threshold k = c
+                    ab = __reduce_add_sync(0xffffffffu, ab);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0 && ab) {                                  // ab == 0 <=> sq == 0
+                        if (prm.babs != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(prm.babs) + item * nthr + (c - 1), static_cast<unsigned long long>(ab));
+                        if (prm.bsq != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(prm.bsq) + item * nthr + (c - 1), sq);
+                    }
+                    if (valid && prm.bnd_t != nullptr) {
+                        const long long o = (item * nthr + (c - 1)) * static_cast<long long>(W) + x;
+                        *reinterpret_cast<int4*>(prm.bnd_t + o) = make_int4(H - get[0], H - get[1], H - get[2], H - get[3]);
+                        *reinterpret_cast<int4*>(prm.bnd_p + o) = make_int4(H - gep[0], H - gep[1], H - gep[2], H - gep[3]);
+                    }
+                }
+            }
+        }
+        if (prm.counts != nullptr) {
+#pragma unroll 1
+            for (int i = lane; i < 256; i += 32) {
+                const uint32_t v = counts[i];
+                const int t = i >> 4, p = i & 15;
+                if (v && t < K && p < K) atomicAdd(prm.counts + item * K * K + t * K + p, static_cast<unsigned long long>(v));
+            }
+        }
+        if (prm.first_pos != nullptr) {
+            // lane l ends up with the minimum over the lanes of row l = map * K + class
+            uint32_t mine = OCTM_NO_SEED;
+#pragma unroll 1
+            for (int r = 0; r < 2 * K; ++r) {
+                const uint32_t v = __reduce_min_sync(0xffffffffu, fst[r * 32]);
+                if (lane == r) mine = v;
+            }
+            if (lane < 2 * K && mine != OCTM_NO_SEED) atomicMin(prm.first_pos + item * 2 * K + lane, mine);
+        }
+        if (prm.unsorted != nullptr) {
+            uns = __reduce_or_sync(0xffffffffu, uns);
+            if (lane == 0 && uns) atomicOr(prm.unsorted + item, uns);
+        }
+        __syncwarp();
     }
 }
 
@@ -1027,10 +1256,18 @@ static int dispatch_np(const LabelPassParams& p, cudaStream_t stream) {
 }
 
 static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
+    // K <= 16 with 4-byte rows: the warp-per-strip kernel; anything else the byte-wise one
+    static const bool env_wide = [] { const char* e = getenv("OCTM_LP_WIDE"); return !(e && e[0] == '0'); }();
+    const bool wide = env_wide && p.W % 4 == 0 && reinterpret_cast<uintptr_t>(p.yt) % 4 == 0 && reinterpret_cast<uintptr_t>(p.yp) % 4 == 0 &&
+                      (p.bnd_t == nullptr || (reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0 && reinterpret_cast<uintptr_t>(p.bnd_p) % 16 == 0)) &&
+                      p.H <= 16383 && static_cast<long long>(p.H) * p.W < (1ll << 32) &&
+                      // a handful of items (one volume) is latency-bound either way: the byte-wise kernel's 32-column warps
+                      // then give four times as many walkers (cfg2, 49 items: 0.09 against 0.21 ms)
+                      p.n_items * ((p.W + 127) / 128) >= 2ll * sm_count() * kWideWarps;
     // few items: one CTA per 256-column strip, partial results joined by atomics on zero-initialised outputs
     const long long resident = static_cast<long long>(sm_count()) * 8;
-    const int strips = p.n_items < resident && p.W > 256 ? (p.W + 255) / 256 : 1;
-    if (strips > 1) {
+    const int strips = wide ? (p.W + 127) / 128 : (p.n_items < resident && p.W > 256 ? (p.W + 255) / 256 : 1);
+    if (wide || strips > 1) {
         const size_t n = static_cast<size_t>(p.n_items), k = static_cast<size_t>(p.K);
         bool ok = true;
         if (p.counts) ok = ok && cudaMemsetAsync(p.counts, 0, n * k * k * 8, stream) == cudaSuccess;
@@ -1042,6 +1279,21 @@ static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
     }
     if (p.unsorted != nullptr && cudaMemsetAsync(p.unsorted, 0, static_cast<size_t>(p.n_items) * 4, stream) != cudaSuccess)
         return fail(OCTM_ERR_LAUNCH, "memset of the label-pass outputs failed");
+    if (wide) {
+        int fit = 0;
+        const int kWideSmem = kWideWarps * wide_warp_bytes(p.K);
+        if (cudaFuncSetAttribute(label_pass_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideWarps * wide_warp_bytes(16)) != cudaSuccess)
+            return fail(OCTM_ERR_LAUNCH, "cudaFuncSetAttribute(label_pass_wide) failed");
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, label_pass_wide, kWideWarps * 32, kWideSmem) != cudaSuccess || fit < 1) {
+            cudaGetLastError();
+            fit = 3;
+        }
+        long long grid = (p.n_items * strips + kWideWarps - 1) / kWideWarps;
+        const long long cap = static_cast<long long>(sm_count()) * fit;
+        if (grid > cap) grid = cap;
+        OCTM_TIMED("label_pass_wide", stream) label_pass_wide<<<static_cast<unsigned>(grid), kWideWarps * 32, kWideSmem, stream>>>(p, strips);
+        return check_launch("label_pass_wide");
+    }
     long long grid = p.n_items * strips;
     if (grid > resident) grid = resident;
     OCTM_TIMED("label_pass_generic", stream) label_pass_generic<<<static_cast<unsigned>(grid), 256, 0, stream>>>(p, strips);
@@ -1107,7 +1359,11 @@ extern "C" int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y
 }
 
 extern "C" int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred) {
-    return octm::fast_ok(H, W, num_classes, y_true, y_pred) ? 1 : 0;
+    if (octm::fast_ok(H, W, num_classes, y_true, y_pred)) return 1;
+    return W % 4 == 0 && reinterpret_cast<uintptr_t>(y_true) % 4 == 0 && reinterpret_cast<uintptr_t>(y_pred) % 4 == 0 && H <= 16383 &&
+                   static_cast<long long>(H) * W < (1ll << 32)
+               ? 2
+               : 0;
 }
 
 extern "C" int octm_confusion_u8(const uint8_t* y_true, const uint8_t* y_pred, int64_t n_items, int64_t item_elems,

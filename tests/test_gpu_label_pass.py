@@ -78,7 +78,8 @@ def test_fast_kernel_layered_and_random(cuda, shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 33, 50, 16), (3, 17, 23, 2), (1, 496, 1024, 10), (2, 21, 300, 12), (2, 5, 7, 9), (1, 1, 1, 2),
-                                   (2, 64, 96, 11)])
+                                   (2, 64, 96, 11), (2, 33, 52, 16), (3, 70, 132, 9), (1, 600, 260, 13), (40, 9, 4, 10),
+                                   (2, 1, 128, 16), (2, 496, 500, 8)])
 def test_generic_kernel(cuda, shape):
     """Ragged widths and K > 8 go through the generic kernel."""
     n, h, w, k = shape
@@ -139,3 +140,29 @@ def test_derived_ratios_match_oracle(cuda):
         for name in lo.COUNT_METRICS + ("thickness_difference", "boundary_mse", "boundary_rmse", "boundary_mad"):
             np.testing.assert_allclose(m[name][i], ref[name], rtol=1e-6, atol=0, err_msg=name)
             assert np.array_equal(m[name][i], ref[name]), name      # in practice bit-identical
+
+
+def test_wide_and_bytewise_kernels_agree_on_paths_and_results(cuda):
+    """K > 8: W % 4 == 0 takes the warp-per-strip kernel (path 2), other widths and unaligned views the byte-wise one (0)"""
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib, suite
+    lib = _lib.load()
+    assert lib.octm_label_pass_path(496, 1024, 10, 0, 0) == 2
+    assert lib.octm_label_pass_path(496, 1022, 10, 0, 0) == 0
+    assert lib.octm_label_pass_path(496, 512, 8, 0, 0) == 1
+    yt, yp = synth.layered_pair(3, 120, 264, 10, seed=77, noise=0.02, min_gap=1)
+    yt[1, 5, 7] = 200                                       # a label >= K: dropped, never aliased
+    a = suite.label_pass(torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda), 10, counts=True, columns=True, seeds=True,
+                         boundaries=True, certify=True)
+    # the same maps as unaligned views (offset by one byte): the byte-wise kernel
+    buf_t = torch.zeros(yt.size + 1, dtype=torch.uint8, device=cuda)
+    buf_p = torch.zeros(yp.size + 1, dtype=torch.uint8, device=cuda)
+    buf_t[1:] = torch.from_numpy(yt).to(cuda).reshape(-1)
+    buf_p[1:] = torch.from_numpy(yp).to(cuda).reshape(-1)
+    vt, vp = buf_t[1:].view(yt.shape), buf_p[1:].view(yp.shape)
+    assert lib.octm_label_pass_path(120, 264, 10, vt.data_ptr(), vp.data_ptr()) == 0
+    b = suite.label_pass(vt, vp, 10, counts=True, columns=True, seeds=True, boundaries=True, certify=True)
+    for name in ("counts", "thick_absdiff", "bnd_sq", "bnd_abs", "bnd_true", "bnd_pred", "first_pos", "unsorted"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert torch.equal(x, y), name
+    assert int(a.counts[1].sum()) == 120 * 264 - 1
