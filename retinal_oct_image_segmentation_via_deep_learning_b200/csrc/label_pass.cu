@@ -28,6 +28,8 @@
 //     histograms -> K x K counts; the strips of an item meet in the zero-initialised outputs through
 //     global reductions (a few dozen RED per warp and item), never at a CTA barrier.
 //
+// WIDE KERNEL (K <= 16, W % 4 == 0): warp per 128-column strip, run-length scan with per-lane run queues drained in
+// lockstep (label_pass_wide below).
 // GENERIC KERNEL: any H, W, K <= 16: thread per column, run-length accumulation down the column.
 #include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
@@ -845,19 +847,25 @@ __global__ void __launch_bounds__(256, OCTM_GEN_MINB) label_pass_generic(const L
 //     warp-instructions per pixel pair, the same as the byte-wise kernel);
 //   * column arithmetic, boundary rows (16-byte stores) and seeds follow per job; warps never meet: their results
 //     join in zero-initialised outputs through global atomics (a few hundred per 63 k pixel pairs).
-constexpr int kWideWarps = 2;
-constexpr int kWideQueue = 64;       // queue entries per lane; a batch of 8 rows pushes at most 32
+#ifndef OCTM_WIDE_WARPS
+#define OCTM_WIDE_WARPS 2
+#endif
+#ifndef OCTM_WIDE_QUEUE
+#define OCTM_WIDE_QUEUE 48
+#endif
+constexpr int kWideWarps = OCTM_WIDE_WARPS;
+constexpr int kWideQueue = OCTM_WIDE_QUEUE;       // queue entries per lane; a batch of 8 rows pushes at most 32
 // per warp: counts u32 [256] | cls u16 [2][K][128] | queue u32 [kWideQueue][32] | fst u32 [2 K][32] | colstate u32 [4][32]
 // (sized by K: 17 KB per warp at K = 10 -> 12 warps per SM)
 static inline int wide_warp_bytes(int K) { return 1024 + 512 * K + kWideQueue * 128 + 256 * K + 512; }
 #ifndef OCTM_WIDE_MINB
-#define OCTM_WIDE_MINB 5
+#define OCTM_WIDE_MINB 7
 #endif
 #ifndef OCTM_WIDE_ROWS
 #define OCTM_WIDE_ROWS 8
 #endif
 #ifndef OCTM_WIDE_PIPE
-#define OCTM_WIDE_PIPE 1
+#define OCTM_WIDE_PIPE 2
 #endif
 __global__ void __launch_bounds__(kWideWarps * 32, OCTM_WIDE_MINB) label_pass_wide(const LabelPassParams prm, const int strips) {
     extern __shared__ __align__(16) unsigned char s_wide[];
@@ -958,7 +966,22 @@ __global__ void __launch_bounds__(kWideWarps * 32, OCTM_WIDE_MINB) label_pass_wi
                     }
                 }
             };
-#if OCTM_WIDE_PIPE
+#if OCTM_WIDE_PIPE == 2
+            // three register batches: two are in flight while one is worked on
+            uint32_t tb[kRows], pb[kRows], tc[kRows], pc[kRows];
+            fetch(tb, pb, kRows);
+            for (int y0 = 0; y0 < H; y0 += 3 * kRows) {
+                fetch(tc, pc, y0 + 2 * kRows);
+                work(ta, pa, y0);
+                if (__any_sync(0xffffffffu, qn > kWideQueue - 4 * kRows)) drain();
+                fetch(ta, pa, y0 + 3 * kRows);
+                work(tb, pb, y0 + kRows);
+                if (__any_sync(0xffffffffu, qn > kWideQueue - 4 * kRows)) drain();
+                fetch(tb, pb, y0 + 4 * kRows);
+                work(tc, pc, y0 + 2 * kRows);
+                if (__any_sync(0xffffffffu, qn > kWideQueue - 4 * kRows)) drain();
+            }
+#elif OCTM_WIDE_PIPE
             // two register batches: the loads of the next one are in flight while this one is worked on
             uint32_t tb[kRows], pb[kRows];
             for (int y0 = 0; y0 < H; y0 += 2 * kRows) {

@@ -48,6 +48,10 @@ def _check_one(yt, yp, k, cuda, certify):
     fp = out.first_pos.cpu().numpy().view(np.uint32)
     np.testing.assert_array_equal(fp[:, 0], _first_pos_oracle(yt, k))
     np.testing.assert_array_equal(fp[:, 1], _first_pos_oracle(yp, k))
+    if certify and yt.shape[1] <= 504:          # (the strip kernel reports taller items unsorted without looking)
+        want = ((np.diff(yt.astype(np.int16), axis=1) < 0).any(axis=(1, 2)).astype(np.uint32)
+                | ((np.diff(yp.astype(np.int16), axis=1) < 0).any(axis=(1, 2)).astype(np.uint32) << 1))
+        np.testing.assert_array_equal(out.unsorted.cpu().numpy().view(np.uint32), want)
 
 
 def test_golden_suite(cuda, golden_dir):
@@ -142,6 +146,21 @@ def test_derived_ratios_match_oracle(cuda):
             assert np.array_equal(m[name][i], ref[name]), name      # in practice bit-identical
 
 
+@pytest.mark.parametrize("shape", [(600, 9, 4, 10), (300, 33, 132, 16), (150, 70, 520, 9), (1200, 1, 128, 16), (80, 120, 1024, 10),
+                                   (700, 17, 52, 12), (640, 40, 100, 8)])
+def test_wide_kernel(cuda, shape):
+    """K <= 16, W % 4 == 0 and enough strips of work (>= 4 per SM): label_pass_wide (run queues drained in lockstep)"""
+    n, h, w, k = shape
+    assert n * ((w + 127) // 128) >= 592
+    yt, yp = synth.random_pair(n, h, w, k, seed=h + 31 * w)
+    _check(yt, yp, k, cuda)
+    if h >= 2 * k:
+        yt, yp = synth.layered_pair(n, h, w, k, seed=h * w, noise=0.02, min_gap=1)
+        _check(yt, yp, k, cuda)
+        yt, yp = synth.layered_pair(n, h, w, k, seed=h * w + 1, noise=0.0, min_gap=1)     # clean: certificate says sorted
+        _check(yt, yp, k, cuda)
+
+
 def test_wide_and_bytewise_kernels_agree_on_paths_and_results(cuda):
     """K > 8: W % 4 == 0 takes the warp-per-strip kernel (path 2), other widths and unaligned views the byte-wise one (0)"""
     import torch
@@ -150,8 +169,10 @@ def test_wide_and_bytewise_kernels_agree_on_paths_and_results(cuda):
     assert lib.octm_label_pass_path(496, 1024, 10, 0, 0) == 2
     assert lib.octm_label_pass_path(496, 1022, 10, 0, 0) == 0
     assert lib.octm_label_pass_path(496, 512, 8, 0, 0) == 1
-    yt, yp = synth.layered_pair(3, 120, 264, 10, seed=77, noise=0.02, min_gap=1)
+    yt, yp = synth.layered_pair(250, 120, 264, 10, seed=77, noise=0.02, min_gap=1)     # 750 strips: the wide kernel
     yt[1, 5, 7] = 200                                       # a label >= K: dropped, never aliased
+    yp[2, 100, 263] = 16
+    yp[3, 0, 0] = 11
     a = suite.label_pass(torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda), 10, counts=True, columns=True, seeds=True,
                          boundaries=True, certify=True)
     # the same maps as unaligned views (offset by one byte): the byte-wise kernel
