@@ -513,22 +513,28 @@ def run_b200(args):
             "uniform_random": (torch.randint(0, K, (m, H, W), generator=g, device=dev, dtype=torch.uint8),
                                torch.randint(0, K, (m, H, W), generator=g, device=dev, dtype=torch.uint8)),
         }
+        # a 10-class label set at HC-MS geometry (496 x 1024): the K <= 16 label pass (label_pass_wide) + the same contour stage
+        kk = {vname: K for vname in variants}
+        variants["k10_496x1024"] = synth.layered_pair_device(min(n, 2048), 496, 1024, 10, seed=7003 + rank, device=dev, noise=0.0)
+        kk["k10_496x1024"] = 10
         for vname, (a, b) in variants.items():
+            K2, m = kk[vname], a.shape[0]
             for _ in range(2):
-                odist.dataset_totals_async(suite.evaluate(a, b, K, contours=contours), world).result()
+                odist.dataset_totals_async(suite.evaluate(a, b, K2, contours=contours), world).result()
             barrier()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             reps = 3
             for _ in range(reps):
-                p2 = odist.dataset_totals_async(suite.evaluate(a, b, K, contours=contours), world)
+                p2 = odist.dataset_totals_async(suite.evaluate(a, b, K2, contours=contours), world)
             s1.record()
             barrier()
             p2.result()
             tv = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-            secondary[vname] = {"value": world * m * reps / (float(tv.item()) / 1e3), "unit": unit, "items_per_gpu": m}
+            secondary[vname] = {"value": world * m * reps / (float(tv.item()) / 1e3), "unit": unit, "items_per_gpu": m,
+                                "shape": [int(a.shape[1]), int(a.shape[2])], "num_classes": K2}
         del variants
 
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None   # device-timed + e2e regions

@@ -2036,10 +2036,14 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
         if (PASS == 1) {
             // per map: 0 = no contour, count = verified height function, kTraceTodo = left to the fallback kernels
             const uint32_t c0 = static_cast<uint32_t>(W) + s_cnt[0], c1 = static_cast<uint32_t>(W) + s_cnt[1];
+            const bool v0 = s_ok[0] && s_minkey[0] == s_seed[0], v1 = s_ok[1] && s_minkey[1] == s_seed[1];
+            // max_pts bounds what is STORED (vertex lists, rows): a pair with two verified sides is measured from the tables
+            // and stores nothing, so its contours may be longer (wide images: 2 W + sum |dh| vertices); 16-bit counters
+            const bool both = v0 && v1 && s_seed[0] != OCTM_NO_SEED && s_seed[1] != OCTM_NO_SEED && c0 <= 0xffffu && c1 <= 0xffffu;
             n0 = s_seed[0] == OCTM_NO_SEED ? 0u
-                 : (s_ok[0] && s_minkey[0] == s_seed[0] && c0 <= static_cast<uint32_t>(prm.max_pts) ? (c0 | kLayeredBit) : kTraceTodo);
+                 : (v0 && (both || c0 <= static_cast<uint32_t>(prm.max_pts)) ? (c0 | kLayeredBit) : kTraceTodo);
             n1 = s_seed[1] == OCTM_NO_SEED ? 0u
-                 : (s_ok[1] && s_minkey[1] == s_seed[1] && c1 <= static_cast<uint32_t>(prm.max_pts) ? (c1 | kLayeredBit) : kTraceTodo);
+                 : (v1 && (both || c1 <= static_cast<uint32_t>(prm.max_pts)) ? (c1 | kLayeredBit) : kTraceTodo);
         }
         const bool todo0 = n0 == kTraceTodo, todo1 = n1 == kTraceTodo;        // PASS 2: cannot happen (the walk settles them)
         const bool lay0 = !todo0 && (n0 & kLayeredBit), lay1 = !todo1 && (n1 & kLayeredBit);
@@ -2194,11 +2198,14 @@ __global__ void __launch_bounds__(kLdWarps * 32, PASS == 1 ? OCTM_LD_MINB : 8) l
                 }
                 continue;
             }
-            if constexpr (PASS == 1) if (!(badbits & 4u)) {
+            // (a side longer than max_pts was accepted because nothing had to be stored; now something may: it is handed
+            // on as unverified, and the walk reports the overflow)
+            const bool over0 = cnt0 > static_cast<uint32_t>(prm.max_pts), over1 = cnt1 > static_cast<uint32_t>(prm.max_pts);
+            if constexpr (PASS == 1) if (!(badbits & 4u) || over0 || over1) {
                 // distances the counters cannot hold: PASS 2 measures the pair again with the wide counting below
                 for (int i = tid; i < kCountBins; i += kLdWarps * 32) bins2[i] = 0;
                 if (tid < 2) {
-                    prm.n_pts[pair * 2 + tid] = tid ? n1 : n0;
+                    prm.n_pts[pair * 2 + tid] = tid ? (over1 ? kTraceTodo : n1) : (over0 ? kTraceTodo : n0);
                     prm.max_sq[pair * 2 + tid] = kNeedsSearch;
                 }
                 if (tid == 2) atomicAdd(prm.todo_count, 1u);

@@ -18,8 +18,15 @@ import torch
 
 from . import _lib, derive
 
-DEFAULT_MAX_PTS = 2048       # contour vertices kept per (item, class, map) on the first attempt
+DEFAULT_MAX_PTS = 2048       # contour vertices kept per (item, class, map) on the first attempt (at least; see default_max_pts)
 MAX_MAX_PTS = 1 << 16        # bound of the retry for items whose contour overflowed max_pts (8 B of scratch per vertex)
+
+
+def default_max_pts(width):
+    """First-attempt vertex bound: a layer boundary crossing a W-pixel image has 2 W + sum |dh| vertices (2.7 W on the
+    synthetic layers), so the bound grows with the width -- 2048 up to W = 512, 4 W beyond (a 1024-wide HC-MS B-scan would
+    otherwise overflow on every contour and be redone)."""
+    return max(DEFAULT_MAX_PTS, min(MAX_MAX_PTS, 4 * int(width)))
 CONTOUR_CHUNK_BYTES = 4 << 30   # vertex + squared-distance scratch per chunk of items (grow-only, reused)
 
 
@@ -286,7 +293,7 @@ def _contour_chunk(yt, yp, k, first_pos, max_pts, want_verts, want_sq, timers=No
     return ContourOut(n_pts, flags, max_sq, p95, sums, verts if want_verts else None, sq if want_sq else None, max_pts)
 
 
-def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT_MAX_PTS, return_vertices=False,
+def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=None, return_vertices=False,
                  return_sq=False, timers=None, check_overflow=True, boundaries=None, unsorted=None):
     """Contour ``[0]`` of every class mask of both maps, then hausdorff / hd95 / assd integers.
 
@@ -300,7 +307,7 @@ def contour_pass(y_true, y_pred, num_classes, first_pos=None, *, max_pts=DEFAULT
     yt, yp = _check_pair(y_true, y_pred)
     n, h, w = yt.shape
     k = int(num_classes)
-    max_pts = (int(max_pts) + 3) & ~3
+    max_pts = (int(default_max_pts(w) if max_pts is None else max_pts) + 3) & ~3
     if h < 2 or w < 2:
         raise ValueError("Input array must be at least 2x2.")     # skimage's message for find_contours
     dev = yt.device
@@ -492,7 +499,7 @@ class SuiteResult:
         return m
 
 
-def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=DEFAULT_MAX_PTS, timers=None,
+def evaluate(y_true, y_pred, num_classes, *, contours=True, boundaries=False, max_pts=None, timers=None,
              validate=True):
     """The full suite on a batch of label maps: fused label pass, contour kernels, float64 epilogue.
 
@@ -551,7 +558,7 @@ def _pinned(nbytes):
 
 
 def evaluate_host(y_true, y_pred, num_classes, *, contours=True, device=None, chunk_items=None,
-                  max_pts=DEFAULT_MAX_PTS, pack=False, pack_threads=0, validate=True):
+                  max_pts=None, pack=False, pack_threads=0, validate=True):
     """The full suite on HOST label maps (numpy arrays or CPU torch tensors, ideally pinned).
 
     Items are streamed to the GPU in chunks through two staging buffers: the host->device copy of

@@ -79,3 +79,35 @@ def test_random_maps_are_never_certified(cuda):
     z = np.zeros((2, 64, 128), np.uint8)                  # constant maps are sorted
     got, _ = _run(z, z, 4, cuda)
     assert (got == 0).all()
+
+
+def test_verified_pairs_do_not_depend_on_max_pts_and_wide_images_need_no_retry(cuda):
+    """A pair with two certified sides is measured from the boundary rows and stores nothing: max_pts (what is STORED per
+    contour) must not matter.  Noisy pairs with a tiny bound go through the overflow retry and end with the same numbers.
+    A 1024-wide B-scan (2 W + sum |dh| > 2048 vertices per contour) must not overflow with the default bound."""
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import suite, synth
+    for noise in (0.0, 1e-4):
+        yt, yp = synth.layered_pair(5, 496, 512, 8, seed=31, noise=noise)
+        t, p = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+        a = suite.evaluate(t, p, 8, max_pts=2048)
+        b = suite.evaluate(t, p, 8, max_pts=256)
+        ma, mb = a.metrics(), b.metrics()
+        # integers bit-exact; the float64 distance sums are added in a path-dependent order (1e-12 relative)
+        for name in ("hausdorff_distance", "hausdorff_distance_95"):
+            np.testing.assert_array_equal(ma[name], mb[name], err_msg=f"{name} noise {noise}")
+        np.testing.assert_allclose(ma["assd"], mb["assd"], rtol=1e-12, atol=0, err_msg=f"assd noise {noise}")
+        ia, ib = a.integers(), b.integers()
+        for name in ("contour_max_sq", "contour_p95_sq"):
+            np.testing.assert_array_equal(ia[name], ib[name], err_msg=f"{name} noise {noise}")
+        np.testing.assert_allclose(ia["contour_sum_dist"], ib["contour_sum_dist"], rtol=1e-12, atol=0)
+        if noise == 0.0:
+            assert int(ib["contour_n_pts"].max()) > 256                          # longer than the bound, and still exact
+    yt, yp = synth.layered_pair(3, 496, 1024, 10, seed=32, noise=0.0)
+    t, p = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+    with_default = suite.evaluate(t, p, 10)
+    assert with_default.contours.max_pts == 4096
+    ref = suite.evaluate(t, p, 10, max_pts=8192)
+    for name in ("hausdorff_distance", "hausdorff_distance_95", "assd"):
+        np.testing.assert_allclose(with_default.metrics()[name], ref.metrics()[name], rtol=1e-12, atol=0, err_msg=name)
+    assert int(with_default.integers()["contour_n_pts"].max()) > 2048
