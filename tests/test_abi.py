@@ -55,9 +55,11 @@ def test_fast_path_predicate(lib):
     so = lib.load()
     assert so.octm_label_pass_path(496, 512, 8, 0, 0) == 1
     assert so.octm_label_pass_path(496, 768, 8, 0, 0) == 1
-    assert so.octm_label_pass_path(496, 1024, 10, 0, 0) == 0      # K > 8 -> generic kernel
-    assert so.octm_label_pass_path(33, 50, 4, 0, 0) == 0          # ragged width
-    assert so.octm_label_pass_path(496, 512, 8, 8, 0) == 0        # misaligned pointer
+    assert so.octm_label_pass_path(496, 1024, 10, 0, 0) == 2      # K > 8 -> warp-per-strip run-length kernel (K <= 16, W % 4 == 0)
+    assert so.octm_label_pass_path(496, 500, 8, 0, 0) == 2        # W % 16 != 0 but W % 4 == 0
+    assert so.octm_label_pass_path(33, 50, 4, 0, 0) == 0          # ragged width -> byte-wise generic kernel
+    assert so.octm_label_pass_path(496, 512, 8, 8, 0) == 2        # 8-byte aligned only: not the TMA kernel
+    assert so.octm_label_pass_path(496, 512, 8, 1, 0) == 0        # misaligned pointer
 
 
 def test_sass_uses_tma_tile_copies(lib):
