@@ -513,6 +513,8 @@ def run_b200(args):
             "uniform_random": (torch.randint(0, K, (m, H, W), generator=g, device=dev, dtype=torch.uint8),
                                torch.randint(0, K, (m, H, W), generator=g, device=dev, dtype=torch.uint8)),
         }
+        # ragged predicted boundaries (one-pixel teeth and overhangs along every layer): most predicted contours are walked
+        variants["ragged_boundaries"] = synth.ragged_pair_device(m, H, W, K, seed=7004 + rank, device=dev)
         # a 10-class label set at HC-MS geometry (496 x 1024): the K <= 16 label pass (label_pass_wide) + the same contour stage
         kk = {vname: K for vname in variants}
         variants["k10_496x1024"] = synth.layered_pair_device(min(n, 2048), 496, 1024, 10, seed=7003 + rank, device=dev, noise=0.0)

@@ -172,6 +172,24 @@ def layered_pair_device(n, h, w, num_classes, seed, device, jitter=1.5, noise=0.
     return y_true, y_pred
 
 
+def ragged_pair_device(n, h, w, num_classes, seed, device, frac=0.5, chunk=4096):
+    """Layered pair whose PREDICTION has ragged boundaries, the way a network's argmax does: every predicted pixel takes,
+    with probability ``frac / 2`` each, the label of its upper or of its lower neighbour.  Interiors stay intact (the
+    neighbours agree there); along every boundary the path gets one-pixel teeth, overhangs and detached single pixels,
+    so most columns of the prediction are out of class order and most predicted contours are not height functions."""
+    import torch
+    y_true, y_pred = layered_pair_device(n, h, w, num_classes, seed, device, chunk=chunk)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 12345)
+    for s in range(0, n, chunk):
+        p = y_pred[s:s + chunk]
+        r = torch.rand(p.shape, generator=g, device=device)
+        up = torch.cat([p[:, :1], p[:, :-1]], dim=1)
+        down = torch.cat([p[:, 1:], p[:, -1:]], dim=1)
+        y_pred[s:s + chunk] = torch.where(r < frac / 2, up, torch.where(r < frac, down, p))
+    return y_true, y_pred
+
+
 def layered_volume_pair(d0, d1, d2, num_classes, seed, jitter=1.0):
     """(vol_true, vol_pred) ``uint8 [d0, d1, d2]`` label volumes with depth along axis 0: K-1 smooth
     surfaces ``b_k(x, z)`` stacked top to bottom; the prediction shifts and jitters every surface

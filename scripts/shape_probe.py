@@ -10,7 +10,10 @@ from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib, suite, s
 n, H, W, K = (int(v) for v in sys.argv[1:5])
 noise = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
 dev = torch.device("cuda", 0)
-yt, yp = synth.layered_pair_device(n, H, W, K, seed=7003, device=dev, noise=noise)
+if noise < 0:          # negative "noise": ragged predicted boundaries
+    yt, yp = synth.ragged_pair_device(n, H, W, K, seed=7003, device=dev)
+else:
+    yt, yp = synth.layered_pair_device(n, H, W, K, seed=7003, device=dev, noise=noise)
 for _ in range(3):
     suite.evaluate(yt, yp, K).totals_host()
 with _lib.kernel_profile() as prof:

@@ -300,3 +300,12 @@ def test_empty_batch(cuda):
     assert vec[0] == 0 and np.all(vec[:odist.base_len(6)] == 0) and vec[-1] == 0
     tot = odist.dataset_totals(suite.evaluate(e, e, 6), 1)
     assert tot["n_items"] == 0 and tot["confusion"].sum() == 0
+
+
+def test_cfg4_ragged_predicted_boundaries(cuda):
+    """One-pixel teeth, overhangs and detached pixels along every predicted layer boundary (what an argmax looks like):
+    the prediction is out of class order in most columns and its contours are walked; the numbers must still be the
+    reference's."""
+    import torch
+    yt, yp = synth.ragged_pair_device(2, 496, 512, 8, seed=91, device=cuda)
+    _check_suite_vs_oracle(yt.cpu().numpy(), yp.cpu().numpy(), 8, cuda)
