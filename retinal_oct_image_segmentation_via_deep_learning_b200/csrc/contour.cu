@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(128, OCTM_LAYERED_MINB) trace_layered_kernel(c
                     bad |= off[u] >= lob && off[u] <= hib && ((eb != (off[u] >= ohb)) != inv);
                 }
             }
+            // a window pixel off: not this polyline -- stop here (a ragged contour fails in its first block; running the
+            // remaining blocks only to say "no" cost 0.9 ms per 16,384 ragged predictions)
+            if (__any_sync(0xffffffffu, bad)) { ok = false; break; }
             // vertices of these columns at their left-to-right positions
             const int da = abs(hb - ha), db = abs(hr - hb);
             const uint32_t cnt = valid ? 2u + static_cast<uint32_t>(da + db) : 0u;
