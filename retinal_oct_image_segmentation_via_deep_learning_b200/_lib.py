@@ -40,6 +40,7 @@ SIGNATURES = {
     "octm_label_pass_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P, _P, _P]),
     "octm_label_pass_sorted_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "octm_label_pass_path": (_INT, [_INT, _INT, _INT, _P, _P]),
+    "octm_label_pass_seed_policy": (_INT, [_INT]),
     "octm_validate_labels_u8": (_INT, [_P, _I64, _P, _P]),
     "octm_contour2d_workspace_bytes": (_c.c_size_t, [_I64, _INT, _INT, _INT, _INT]),
     "octm_contour2d_u8": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _INT, _P, _P, _P, _P, _P, _P, _c.c_size_t, _P]),

@@ -34,6 +34,7 @@
 #include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -1323,13 +1324,86 @@ static int launch_generic(const LabelPassParams& p, cudaStream_t stream) {
     return check_launch("label_pass_generic");
 }
 
+// ------------------------------------------------------------------------------------ where the seeds come from
+// With the certificate the strip kernel has two ways to the contour seeds: from the column totals in the item epilogue
+// (free, but the maps the certificate rejects are rescanned by first_pos_fix_kernel: 0.95 ms per 16,384 rejected maps),
+// or tracked per pixel (+0.35 ms per 16,384 items whatever the data).  Clean data wants the first, a stream of
+// predictions that are mostly out of class order (any real argmax) the second.  The choice follows the data: every call
+// leaves "maps rejected / maps seen" in a host-mapped word (one tiny kernel, no synchronisation: the next call reads
+// whatever has arrived), and a call tracks per pixel when more than a fifth of the maps of the last report were
+// rejected.  Both ways give the same seeds (tests run both); octm_label_pass_seed_policy pins one.
+struct SeedFeedback {
+    uint32_t* host = nullptr;      // mapped, pinned: [0] rejected maps, [1] maps
+    uint32_t* dev = nullptr;       // the device's view of it
+};
+static SeedFeedback g_seed_fb[64];
+static std::mutex g_seed_mu;
+static std::atomic<int> g_seed_policy{0};      // 0 follow the data, 1 column totals + rescan, 2 per pixel
+
+static SeedFeedback* seed_feedback() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_seed_mu);
+    SeedFeedback& f = g_seed_fb[dev];
+    if (f.host == nullptr) {
+        void* h = nullptr;
+        void* d = nullptr;
+        if (cudaHostAlloc(&h, 2 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        f.host = static_cast<uint32_t*>(h);
+        f.dev = static_cast<uint32_t*>(d);
+        f.host[0] = f.host[1] = 0;
+    }
+    return &f;
+}
+
+__global__ void __launch_bounds__(1024) seed_feedback_kernel(const uint32_t* __restrict__ unsorted, long long n, uint32_t* out) {
+    __shared__ uint32_t s_sum[32];
+    uint32_t c = 0;
+    for (long long i = threadIdx.x; i < n; i += 1024) c += __popc(unsorted[i] & 3u);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        c = __reduce_add_sync(0xffffffffu, s_sum[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            out[1] = static_cast<uint32_t>(min(2 * n, static_cast<long long>(0xffffffffu)));
+            out[0] = c;
+        }
+    }
+}
+
+static bool seeds_per_pixel() {
+    const int policy = g_seed_policy.load();
+    if (policy != 0) return policy == 2;
+    SeedFeedback* f = seed_feedback();
+    if (f == nullptr) return false;
+    const uint32_t rejected = *static_cast<volatile uint32_t*>(f->host), maps = *static_cast<volatile uint32_t*>(f->host + 1);
+    return maps != 0 && static_cast<unsigned long long>(rejected) * 5ull > maps;
+}
+
+static int report_rejected(const LabelPassParams& p, cudaStream_t stream) {
+    SeedFeedback* f = seed_feedback();
+    if (f == nullptr) return OCTM_OK;
+    OCTM_TIMED("seed_feedback_kernel", stream) seed_feedback_kernel<<<1, 1024, 0, stream>>>(p.unsorted, p.n_items, f->dev);
+    return check_launch("seed_feedback_kernel");
+}
+
 int run_label_pass(const LabelPassParams& p, bool conf, bool cols, bool seeds, cudaStream_t stream) {
     if (p.n_items == 0) return OCTM_OK;
     if (fast_ok(p.H, p.W, p.K, p.yt, p.yp) && p.n_items * p.H < (1ll << 31) /* TMA row coordinate */ &&
         (p.bnd_t == nullptr || reinterpret_cast<uintptr_t>(p.bnd_t) % 16 == 0) &&
         (p.bnd_p == nullptr || reinterpret_cast<uintptr_t>(p.bnd_p) % 16 == 0)) {
         // the suite's call: certificate; seeds (if asked for) from the column totals, rescanned for rejected maps
-        if (p.unsorted != nullptr) return dispatch_np<true, true, false, true>(p, stream);
+        if (p.unsorted != nullptr) {
+            const int e = p.first_pos != nullptr && seeds_per_pixel() ? dispatch_np<true, true, true, true>(p, stream)
+                                                                      : dispatch_np<true, true, false, true>(p, stream);
+            if (e != OCTM_OK || p.first_pos == nullptr) return e;
+            return report_rejected(p, stream);
+        }
         if (conf && cols && seeds) return dispatch_np<true, true, true, false>(p, stream);
         if (conf && cols) return dispatch_np<true, true, false, false>(p, stream);
         if (conf && !cols && !seeds) return dispatch_np<true, false, false, false>(p, stream);
@@ -1379,6 +1453,11 @@ extern "C" int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y
     const bool cols = thick_absdiff || bnd_sq || bnd_abs || bnd_true;
     const bool seeds = first_pos != nullptr;
     return octm::run_label_pass(p, conf, cols, seeds, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int octm_label_pass_seed_policy(int policy) {
+    if (policy < 0 || policy > 2) return octm::g_seed_policy.load();
+    return octm::g_seed_policy.exchange(policy);
 }
 
 extern "C" int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred) {

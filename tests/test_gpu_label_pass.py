@@ -187,3 +187,47 @@ def test_wide_and_bytewise_kernels_agree_on_paths_and_results(cuda):
         x, y = getattr(a, name), getattr(b, name)
         assert torch.equal(x, y), name
     assert int(a.counts[1].sum()) == 120 * 264 - 1
+
+
+def test_seed_policies_give_the_same_seeds(cuda):
+    """The strip kernel's seeds come from the column totals (+ a rescan of rejected maps) or from per-pixel tracking,
+    chosen by the data; both must match the oracle and each other, on clean, noisy and random maps."""
+    import torch
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib, suite
+    lib = _lib.load()
+    before = lib.octm_label_pass_seed_policy(-1)
+    try:
+        for policy in (1, 2, 0):
+            lib.octm_label_pass_seed_policy(policy)
+            assert lib.octm_label_pass_seed_policy(-1) == policy
+            for noise in (0.0, 0.02):
+                yt, yp = synth.layered_pair(5, 496, 512, 8, seed=11 + policy, noise=noise, min_gap=1)
+                _check_one(yt, yp, 8, cuda, True)
+            yt, yp = synth.random_pair(3, 62, 128, 5, seed=12)
+            _check_one(yt, yp, 5, cuda, True)
+        # following the data: a rejected batch switches the next call to per-pixel tracking (no rescan kernel), a clean
+        # batch switches back; the outputs never depend on it
+        lib.octm_label_pass_seed_policy(0)
+        yt, yp = synth.layered_pair(6, 496, 512, 8, seed=21, noise=0.01, min_gap=1)
+        t, p = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+        ct, cp = torch.from_numpy(synth.layered_pair(6, 496, 512, 8, seed=22)[0]).to(cuda), None
+        cp = ct.clone()
+
+        def kernels(a, b):
+            with _lib.kernel_profile() as prof:
+                out = suite.label_pass(a, b, 8, counts=True, columns=True, seeds=True, boundaries=True, certify=True)
+                torch.cuda.synchronize()
+            return out, set(prof.kernels)
+
+        kernels(ct, cp)                                     # clean report
+        o1, k1 = kernels(t, p)                              # decided by the clean report: totals + rescan
+        assert "first_pos_fix_kernel" in k1
+        o2, k2 = kernels(t, p)                              # decided by the noisy report: per pixel
+        assert "first_pos_fix_kernel" not in k2
+        assert torch.equal(o1.first_pos, o2.first_pos) and torch.equal(o1.unsorted, o2.unsorted)
+        assert torch.equal(o1.counts, o2.counts) and torch.equal(o1.bnd_pred, o2.bnd_pred)
+        _, k3 = kernels(ct, cp)                             # still per pixel (the report before was noisy) ...
+        _, k4 = kernels(ct, cp)                             # ... and back
+        assert "first_pos_fix_kernel" not in k3 and "first_pos_fix_kernel" in k4
+    finally:
+        lib.octm_label_pass_seed_policy(before)
