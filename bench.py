@@ -53,6 +53,8 @@ KERNEL_NOTES = {
     # bound + the counter that shows it (ncu summaries under profiles/)
     "label_pass_fast": ("hbm", "dram read = algorithmic bytes (ratio 1.01); issue-active 70.5 %, 109 k warp-instructions per B-scan: in-order issue at 4 warps/scheduler, 128 registers (r2)"),
     "label_pass_generic": ("latency", "thread-per-column run-length scan (any shape, small batches of K > 8); 1.46 TB/s at scale (r2), latency-bound on one volume"),
+    "layered_distance_kernel_rows": ("issue", "PASS 1's code for a lightly noisy stream: sides of rejected maps are re-centred rows from the pixel verification, measured table x table like certified ones"),
+    "walk_report_kernel": ("latency", "one thread: contours walked / contours -> a host-mapped word that picks the next call's step order (noisy streams only)"),
     "seed_feedback_kernel": ("latency", "one CTA: maps the certificate rejected / maps seen -> a host-mapped word that picks the next call's seed source"),
     "label_pass_wide": ("latency", "warp per 128-column strip, run queues drained in lockstep (K <= 16, W % 4 == 0): 2.6 TB/s at 2048 x 496x1024 K=10; issue-active 39 %, 10-14 warps per SM by shared memory (r2)"),
     "first_pos_fix_kernel": ("hbm", "rescans only the maps the layering certificate rejected (nothing on clean data): 3.9 TB/s of those maps"),

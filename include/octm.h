@@ -138,10 +138,12 @@ OCTM_API int octm_label_pass_sorted_u8(const uint8_t* y_true, const uint8_t* y_p
  * 4-byte aligned maps), 0 = byte-wise generic kernel. */
 OCTM_API int octm_label_pass_path(int H, int W, int num_classes, const void* y_true, const void* y_pred);
 
-/* Where octm_label_pass_sorted_u8's strip kernel takes the contour seeds from: 0 = follow the data (default: column
- * totals + a rescan of the maps the certificate rejects while those are few, per-pixel tracking once more than a fifth of
- * the maps of the previous call were rejected), 1 = always column totals + rescan, 2 = always per pixel.  Same seeds
- * either way; only the time differs.  Returns the previous policy (any other argument: just reports it). */
+/* What the suite's kernels assume about the stream of label maps -- a speed heuristic, never a difference in results:
+ * 0 = follow the data (default: every certified label pass reports how many maps its certificate rejected; the next calls
+ * assume a noisy stream once that was more than a fifth), 1 = assume clean (seeds from the column totals + a rescan of
+ * rejected maps; contour stage: boundary-row pass first), 2 = assume noisy (seeds tracked per pixel; contour stage: the
+ * rejected maps' contours are verified against the label pixels first so that the fast pass can measure them).
+ * Returns the previous policy (any other argument: just reports it). */
 OCTM_API int octm_label_pass_seed_policy(int policy);
 
 /* max label over the whole tensor -> *max_label (device uint32); for input validation. */

@@ -60,6 +60,9 @@ struct ProfScope {
 #define OCTM_TIMED(name, stream) for (octm::ProfScope octm_ps_(name, stream); octm_ps_.once();)
 
 int sm_count();            // SMs of the current device (cached per device)
+// label_pass.cu: did the certificate reject more than a fifth of the maps of the last certified label pass on this device
+// (or is that pinned by octm_label_pass_seed_policy)?  Speed heuristics only: results never depend on it.
+bool stream_mostly_rejected();
 int max_optin_smem();      // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device
 
 #ifdef __CUDACC__

@@ -1376,7 +1376,9 @@ __global__ void __launch_bounds__(1024) seed_feedback_kernel(const uint32_t* __r
     }
 }
 
-static bool seeds_per_pixel() {
+bool stream_mostly_rejected();
+static bool seeds_per_pixel() { return stream_mostly_rejected(); }
+bool stream_mostly_rejected() {
     const int policy = g_seed_policy.load();
     if (policy != 0) return policy == 2;
     SeedFeedback* f = seed_feedback();

@@ -309,3 +309,23 @@ def test_cfg4_ragged_predicted_boundaries(cuda):
     import torch
     yt, yp = synth.ragged_pair_device(2, 496, 512, 8, seed=91, device=cuda)
     _check_suite_vs_oracle(yt.cpu().numpy(), yp.cpu().numpy(), 8, cuda)
+
+
+@pytest.mark.parametrize("policy", [1, 2])
+def test_both_stream_policies_give_the_reference_numbers(cuda, policy):
+    """The order of the first contour-stage steps (and the seed source) follows the data; pinned either way, clean,
+    lightly noisy, heavily noisy and ragged pairs must all come out as the oracle says."""
+    from retinal_oct_image_segmentation_via_deep_learning_b200 import _lib
+    lib = _lib.load()
+    before = lib.octm_label_pass_seed_policy(policy)
+    try:
+        for seed, noise in ((41, 0.0), (42, 2e-5), (43, 2e-3)):
+            yt, yp = synth.layered_pair(2, 496, 512, 8, seed=seed, noise=noise)
+            _check_suite_vs_oracle(yt, yp, 8, cuda)
+        yt, yp = synth.ragged_pair_device(2, 496, 512, 8, seed=44, device=cuda)
+        _check_suite_vs_oracle(yt.cpu().numpy(), yp.cpu().numpy(), 8, cuda)
+        yt, yp = synth.layered_pair(2, 496, 512, 8, seed=45, noise=1e-4)
+        yt[0], yp[1] = yp[0].copy(), yt[1].copy()             # the noisy map as y_true (item 0), both clean-ish (item 1)
+        _check_suite_vs_oracle(yt, yp, 8, cuda)
+    finally:
+        lib.octm_label_pass_seed_policy(before)
